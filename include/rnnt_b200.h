@@ -1,0 +1,96 @@
+/* rnnt_b200.h -- C ABI of the B200-native RNN-T transducer head.
+ *
+ * Drop-in boundary for the one hot path this repository accelerates: the RNN-T joint network
+ * (f_t + g_u -> tanh -> Linear(H,V) -> log_softmax) fused with the RNNTLoss alpha/beta lattice and
+ * its gradient, plus the greedy-decode joint step.  The reference (MyrtleSoftware/myrtlespeech) is
+ * pure Python on stock PyTorch and its snapshot contains no RNN-T code, so each entry
+ * point cites the in-tree CTC analog whose role it takes:
+ *
+ *   rnnt_fused_forward / rnnt_fused_backward
+ *       loss module forward + autograd:  src/myrtlespeech/loss/ctc_loss.py:51-101 (LogSoftmax at :95,
+ *       library loss at :96-101), called from src/myrtlespeech/run/train.py:67 and :73; the Linear it
+ *       absorbs is src/myrtlespeech/model/fully_connected.py:118-126,164.
+ *   rnnt_lattice_forward
+ *       the loss alone on materialised log-probabilities (same call sites), for callers that already
+ *       hold a (B,T,U+1,V) tensor.
+ *   rnnt_greedy_joint_argmax
+ *       the per-step argmax of src/myrtlespeech/post_process/ctc_greedy_decoder.py:74, called from
+ *       src/myrtlespeech/run/run.py:94.
+ *
+ * Conventions: plain pointers and sizes only; every device buffer (inputs, outputs, workspace) is
+ * allocated by the caller; calls are stream-ordered on `stream` (a cudaStream_t passed as void*), never
+ * synchronise the host, keep no global mutable state and never allocate.  Return value 0 = success;
+ * otherwise one of RNNT_ERR_* and rnnt_last_error() describes it.  Length arrays are HOST int32 (they
+ * originate on the host: src/myrtlespeech/data/batch.py:103-105); label ids are DEVICE int32
+ * (src/myrtlespeech/builders/task_config.py:103-108).
+ *
+ * Layouts (row-major, contiguous):
+ *   f   bf16 [B][Tmax][H]        encoder output        g   bf16 [B][Umax+1][H]   prediction output
+ *   W   bf16 [V][H]              joint projection      bias f32 [V] (may be NULL)
+ *   y   i32  [B][Umax]           label ids (never `blank`)
+ *   loss f32 [B]                 -ln P(y_b | x_b)
+ *   df  f32 [B][Tmax][H]   dg f32 [B][Umax+1][H]   dW f32 [V][H]   db f32 [V]
+ * Constraints: H % 8 == 0, 1 <= V <= 2048, Umax + 1 <= 1024, 1 <= f_lens[b] <= Tmax, 0 <= y_lens[b] <= Umax.
+ */
+#ifndef RNNT_B200_H_
+#define RNNT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNNT_OK 0
+#define RNNT_ERR_INVALID_ARGUMENT 1
+#define RNNT_ERR_WORKSPACE_TOO_SMALL 2
+#define RNNT_ERR_CUDA 3
+#define RNNT_ERR_UNSUPPORTED 4
+
+/* ABI version of this header (bumped on any signature change). */
+int rnnt_abi_version(void);
+
+/* Human-readable description of the last non-zero return on this thread. */
+const char* rnnt_last_error(void);
+
+/* Bytes of device workspace the fused calls need for these maxima.  Pure host arithmetic. */
+size_t rnnt_fused_workspace_bytes(int B, int Tmax, int Umax, int V, int H);
+
+/* Joint + log-softmax + alpha/beta.  Writes loss[B]; leaves lse / lp_blank / lp_label / arc
+ * occupancies in `workspace` for rnnt_fused_backward.  The B*T*(U+1)*V logits are never written. */
+int rnnt_fused_forward(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+                       const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax,
+                       int V, int H, int blank, float* loss, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* Gradient of sum_b grad_loss[b] * loss[b].  `workspace` must be the one the matching forward filled.
+ * Overwrites df, dg, dW, db. */
+int rnnt_fused_backward(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+                        const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax,
+                        int V, int H, int blank, const float* grad_loss, float* df, float* dg, float* dW,
+                        float* db, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Loss on materialised log-probabilities: lp_blank, lp_label f32 [B][Tmax][Umax+1] (natural layout,
+ * lp_label[b][t][u] = log p(y[b][u] | t,u), column Umax unused).  Writes loss[B] and the arc
+ * occupancies c_blank, c_label f32 [B][Tmax][Umax+1] with
+ *   d loss_b / d logits[b,t,u,k] = softmax_k (c_blank + c_label) - [k==blank] c_blank - [k==y_u] c_label. */
+size_t rnnt_lattice_workspace_bytes(int B, int Tmax, int Umax);
+int rnnt_lattice_forward(const float* lp_blank, const float* lp_label, const int32_t* f_lens_host,
+                         const int32_t* y_lens_host, int B, int Tmax, int Umax, float* loss, float* c_blank,
+                         float* c_label, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One greedy-decode joint step for B utterances: out_k[b] = argmax_v (W . tanh(f[b][t_idx[b]] + g[b]) + bias)
+ * (lowest index wins ties), or -1 where t_idx[b] < 0.  g is bf16 [B][H]; t_idx, out_k are DEVICE int32 [B]. */
+int rnnt_greedy_joint_argmax(const void* f, const void* g, const void* W, const float* bias,
+                             const int32_t* t_idx, int32_t* out_k, int B, int Tmax, int V, int H, void* stream);
+
+/* Debug / test hooks (not part of the drop-in surface). */
+int rnnt_debug_copy_stats(const void* workspace, int B, int Tmax, int Umax, int V, int H, float* lp_blank,
+                          float* lp_label, float* c_blank, float* c_label, float* lnp_beta, void* stream);
+void rnnt_debug_set(const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNNT_B200_H_ */

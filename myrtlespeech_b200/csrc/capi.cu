@@ -1,0 +1,364 @@
+// C ABI (include/rnnt_b200.h): argument validation, workspace carving, TMA tensor maps and the
+// per-slab kernel schedule.  No torch types, no allocation, no host synchronisation.
+//
+// Schedule.  Lattice rows are processed in slabs of `slab_tiles` tiles (one tile per SM).  Per slab
+//   forward : hgen -> joint_fwd                       (h slab stays L2-resident between the two)
+//   backward: hgen -> joint_dz -> joint_dh -> joint_dw (h and dz slabs are L2-resident ring buffers;
+//             the B*T*U*V logits / dlogits tensors never exist in HBM)
+// followed / preceded by the alpha-beta lattice kernels over the whole batch.
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/rnnt_b200.h"
+#include "launch.h"
+
+namespace {
+
+using namespace rnnt;
+
+thread_local char g_err[512] = "";
+int g_dw_desc_mode = 0;
+int g_slab_tiles_override = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(x)                                                                          \
+  do {                                                                                       \
+    cudaError_t e_ = (x);                                                                    \
+    if (e_ != cudaSuccess) return fail(RNNT_ERR_CUDA, "%s -> %s", #x, cudaGetErrorString(e_)); \
+  } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v;
+    else
+      n = 148;
+  }
+  return n;
+}
+
+struct Plan {
+  int B, Tmax, Umax, U1, V, H, Vp, D;
+  int max_tiles, slab_tiles;
+  size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_wt, o_h, o_dz;
+  size_t total;
+};
+
+Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
+  Plan p{};
+  p.B = B; p.Tmax = Tmax; p.Umax = Umax; p.U1 = Umax + 1; p.V = V; p.H = H;
+  p.Vp = static_cast<int>(align_up(V, 64));
+  p.D = Tmax + p.U1;
+  p.max_tiles = B * ((Tmax + kTT - 1) / kTT) * ((p.U1 + kTU - 1) / kTU);
+  p.slab_tiles = g_slab_tiles_override > 0 ? g_slab_tiles_override : 148;
+  if (p.slab_tiles > p.max_tiles) p.slab_tiles = p.max_tiles;
+  const size_t cells = static_cast<size_t>(B) * p.D * p.U1;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
+  p.o_prefix = take(sizeof(int) * (B + 1));
+  p.o_flens = take(sizeof(int) * B);
+  p.o_ylens = take(sizeof(int) * B);
+  p.o_lse = take(sizeof(float) * static_cast<size_t>(p.max_tiles) * kTileRows);
+  p.o_lpb = take(sizeof(float) * cells);
+  p.o_lpl = take(sizeof(float) * cells);
+  p.o_alpha = take(sizeof(float) * cells);
+  p.o_beta = take(sizeof(float) * cells);
+  p.o_c1 = take(sizeof(float) * cells);
+  p.o_c2 = take(sizeof(float) * cells);
+  p.o_lnpb = take(sizeof(float) * B);
+  p.o_wt = take(2 * static_cast<size_t>(H) * p.Vp);
+  p.o_h = take(2 * static_cast<size_t>(p.slab_tiles) * kTileRows * H);
+  p.o_dz = take(2 * static_cast<size_t>(p.slab_tiles) * kTileRows * p.Vp);
+  p.total = o;
+  return p;
+}
+
+int check_dims(int B, int Tmax, int Umax, int V, int H) {
+  if (B < 1 || Tmax < 1 || Umax < 0) return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d Umax=%d out of range", B, Tmax, Umax);
+  if (V < 1 || V > 2048) return fail(RNNT_ERR_UNSUPPORTED, "V=%d must be in [1, 2048]", V);
+  if (H < 8 || H % 8 != 0) return fail(RNNT_ERR_UNSUPPORTED, "H=%d must be a positive multiple of 8", H);
+  if (Umax + 1 > 1024) return fail(RNNT_ERR_UNSUPPORTED, "Umax+1=%d must be <= 1024", Umax + 1);
+  return RNNT_OK;
+}
+
+int check_lens(const int32_t* fl, const int32_t* yl, int B, int Tmax, int Umax) {
+  if (!fl || !yl) return fail(RNNT_ERR_INVALID_ARGUMENT, "length arrays must not be NULL");
+  for (int b = 0; b < B; ++b) {
+    if (fl[b] < 1 || fl[b] > Tmax) return fail(RNNT_ERR_INVALID_ARGUMENT, "f_lens[%d]=%d must be in [1, %d]", b, fl[b], Tmax);
+    if (yl[b] < 0 || yl[b] > Umax) return fail(RNNT_ERR_INVALID_ARGUMENT, "y_lens[%d]=%d must be in [0, %d]", b, yl[b], Umax);
+  }
+  return RNNT_OK;
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows][cols] with `pitch` elements per row; box = box_cols x box_rows, 128B swizzle.
+int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_cols,
+             uint32_t box_rows) {
+  auto enc = get_encode();
+  if (!enc) return fail(RNNT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(RNNT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu pitch=%llu box=%ux%u", (int)r,
+                (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch, box_cols, box_rows);
+  return RNNT_OK;
+}
+
+int chunk_cols(int n) {
+  int nc = (n + 31) / 32 * 32;
+  return nc > 256 ? 256 : nc;
+}
+
+struct Ws {
+  uint8_t* base;
+  const Plan& p;
+  template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
+};
+
+Lattice make_lattice(const Ws& w) {
+  Lattice L{};
+  L.tile_prefix = w.at<int>(w.p.o_prefix);
+  L.f_lens = w.at<int>(w.p.o_flens);
+  L.y_lens = w.at<int>(w.p.o_ylens);
+  L.B = w.p.B; L.Tmax = w.p.Tmax; L.U1max = w.p.U1; L.D = w.p.D;
+  return L;
+}
+
+int upload_lengths(const Ws& w, const int32_t* fl, const int32_t* yl, int* n_tiles_out, cudaStream_t s) {
+  const int B = w.p.B;
+  std::vector<int> prefix(B + 1, 0);
+  for (int b = 0; b < B; ++b)
+    prefix[b + 1] = prefix[b] + ((fl[b] + kTT - 1) / kTT) * ((yl[b] + 1 + kTU - 1) / kTU);
+  *n_tiles_out = prefix[B];
+  // pageable sources: the runtime stages them before returning, so the host buffers may die after the call
+  CUDA_TRY(cudaMemcpyAsync(w.at<int>(w.p.o_prefix), prefix.data(), sizeof(int) * (B + 1), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(w.at<int>(w.p.o_flens), fl, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(w.at<int>(w.p.o_ylens), yl, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+  return RNNT_OK;
+}
+
+int count_tiles(const int32_t* fl, const int32_t* yl, int B) {
+  int n = 0;
+  for (int b = 0; b < B; ++b) n += ((fl[b] + kTT - 1) / kTT) * ((yl[b] + 1 + kTU - 1) / kTU);
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rnnt_abi_version(void) { return 1; }
+
+const char* rnnt_last_error(void) { return g_err; }
+
+void rnnt_debug_set(const char* key, int value) {
+  if (!strcmp(key, "dw_desc_mode")) g_dw_desc_mode = value;
+  if (!strcmp(key, "slab_tiles")) g_slab_tiles_override = value;
+}
+
+size_t rnnt_fused_workspace_bytes(int B, int Tmax, int Umax, int V, int H) {
+  if (check_dims(B, Tmax, Umax, V, H) != RNNT_OK) return 0;
+  return make_plan(B, Tmax, Umax, V, H).total;
+}
+
+int rnnt_fused_forward(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+                       const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax, int V,
+                       int H, int blank, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_dims(B, Tmax, Umax, V, H);
+  if (rc) return rc;
+  if (!f || !g || !W || !loss || !workspace || (Umax > 0 && !y)) return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+  if (blank < 0 || blank >= V) return fail(RNNT_ERR_INVALID_ARGUMENT, "blank=%d must be in [0, %d]", blank, V - 1);
+  rc = check_lens(f_lens_host, y_lens_host, B, Tmax, Umax);
+  if (rc) return rc;
+  const Plan p = make_plan(B, Tmax, Umax, V, H);
+  if (workspace_bytes < p.total)
+    return fail(RNNT_ERR_WORKSPACE_TOO_SMALL, "workspace %zu bytes < required %zu", workspace_bytes, p.total);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Ws w{static_cast<uint8_t*>(workspace), p};
+  int n_tiles = 0;
+  rc = upload_lengths(w, f_lens_host, y_lens_host, &n_tiles, s);
+  if (rc) return rc;
+  const Lattice L = make_lattice(w);
+  JointDims d{V, H, p.Vp, blank, Umax > 0 ? Umax : 1};
+
+  const int nc = chunk_cols(V);
+  CUtensorMap tm_h, tm_w;
+  rc = make_map(&tm_h, w.at<void>(p.o_h), H, static_cast<uint64_t>(p.slab_tiles) * kTileRows, H, 64, 128);
+  if (rc) return rc;
+  rc = make_map(&tm_w, W, H, V, H, 64, nc);
+  if (rc) return rc;
+
+  FwdArgs a{bias, y, w.at<float>(p.o_lse), w.at<float>(p.o_lpb), w.at<float>(p.o_lpl)};
+  for (int t0 = 0; t0 < n_tiles; t0 += p.slab_tiles) {
+    const int nt = (n_tiles - t0 < p.slab_tiles) ? n_tiles - t0 : p.slab_tiles;
+    launch_hgen(L, static_cast<const __nv_bfloat16*>(f), static_cast<const __nv_bfloat16*>(g),
+                w.at<__nv_bfloat16>(p.o_h), t0, nt, H, s);
+    launch_joint_fwd(L, d, tm_h, tm_w, a, t0, nt, nc, s);
+  }
+  launch_lattice_alpha_beta(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl), w.at<float>(p.o_alpha),
+                            w.at<float>(p.o_beta), loss, w.at<float>(p.o_lnpb), s);
+  launch_lattice_coefs(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl), w.at<float>(p.o_alpha), w.at<float>(p.o_beta),
+                       loss, w.at<float>(p.o_c1), w.at<float>(p.o_c2), s);
+  CUDA_TRY(cudaGetLastError());
+  return RNNT_OK;
+}
+
+int rnnt_fused_backward(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+                        const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax, int V,
+                        int H, int blank, const float* grad_loss, float* df, float* dg, float* dW, float* db,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_dims(B, Tmax, Umax, V, H);
+  if (rc) return rc;
+  if (!f || !g || !W || !grad_loss || !df || !dg || !dW || !db || !workspace || (Umax > 0 && !y))
+    return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+  if (blank < 0 || blank >= V) return fail(RNNT_ERR_INVALID_ARGUMENT, "blank=%d must be in [0, %d]", blank, V - 1);
+  rc = check_lens(f_lens_host, y_lens_host, B, Tmax, Umax);
+  if (rc) return rc;
+  const Plan p = make_plan(B, Tmax, Umax, V, H);
+  if (workspace_bytes < p.total)
+    return fail(RNNT_ERR_WORKSPACE_TOO_SMALL, "workspace %zu bytes < required %zu", workspace_bytes, p.total);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Ws w{static_cast<uint8_t*>(workspace), p};
+  const int n_tiles = count_tiles(f_lens_host, y_lens_host, B);
+  const Lattice L = make_lattice(w);
+  JointDims d{V, H, p.Vp, blank, Umax > 0 ? Umax : 1};
+
+  CUDA_TRY(cudaMemsetAsync(df, 0, sizeof(float) * static_cast<size_t>(B) * Tmax * H, s));
+  CUDA_TRY(cudaMemsetAsync(dg, 0, sizeof(float) * static_cast<size_t>(B) * (Umax + 1) * H, s));
+  CUDA_TRY(cudaMemsetAsync(dW, 0, sizeof(float) * static_cast<size_t>(V) * H, s));
+  CUDA_TRY(cudaMemsetAsync(db, 0, sizeof(float) * V, s));
+  launch_transpose_w(static_cast<const __nv_bfloat16*>(W), w.at<__nv_bfloat16>(p.o_wt), V, H, p.Vp, s);
+
+  const int nc_v = chunk_cols(V), nc_h = chunk_cols(H);
+  const uint64_t slab_rows = static_cast<uint64_t>(p.slab_tiles) * kTileRows;
+  CUtensorMap tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn;
+  if ((rc = make_map(&tm_h, w.at<void>(p.o_h), H, slab_rows, H, 64, 128))) return rc;
+  if ((rc = make_map(&tm_w, W, H, V, H, 64, nc_v))) return rc;
+  if ((rc = make_map(&tm_dz, w.at<void>(p.o_dz), p.Vp, slab_rows, p.Vp, 64, 128))) return rc;
+  if ((rc = make_map(&tm_wt, w.at<void>(p.o_wt), p.Vp, H, p.Vp, 64, nc_h))) return rc;
+  if ((rc = make_map(&tm_dz_mn, w.at<void>(p.o_dz), p.Vp, slab_rows, p.Vp, 64, 64))) return rc;
+  if ((rc = make_map(&tm_h_mn, w.at<void>(p.o_h), H, slab_rows, H, 64, 64))) return rc;
+
+  DzArgs za{bias, y, w.at<float>(p.o_lse), w.at<float>(p.o_lpb), w.at<float>(p.o_lpl), w.at<float>(p.o_c1),
+            w.at<float>(p.o_c2), grad_loss, db};
+  DhArgs ha{w.at<__nv_bfloat16>(p.o_h), df, dg};
+  const int n_sm = sm_count();
+  for (int t0 = 0; t0 < n_tiles; t0 += p.slab_tiles) {
+    const int nt = (n_tiles - t0 < p.slab_tiles) ? n_tiles - t0 : p.slab_tiles;
+    launch_hgen(L, static_cast<const __nv_bfloat16*>(f), static_cast<const __nv_bfloat16*>(g),
+                w.at<__nv_bfloat16>(p.o_h), t0, nt, H, s);
+    launch_joint_dz(L, d, tm_h, tm_w, tm_dz, za, t0, nt, nc_v, s);
+    launch_joint_dh(L, d, tm_dz, tm_wt, ha, t0, nt, nc_h, s);
+    launch_joint_dw(d, tm_dz_mn, tm_h_mn, dW, nt, n_sm, g_dw_desc_mode, s);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return RNNT_OK;
+}
+
+size_t rnnt_lattice_workspace_bytes(int B, int Tmax, int Umax) {
+  if (B < 1 || Tmax < 1 || Umax < 0) return 0;
+  const size_t cells = static_cast<size_t>(B) * (Tmax + Umax + 1) * (Umax + 1);
+  return 3 * 1024 + align_up(sizeof(int) * (B + 1), 1024) * 3 + 6 * align_up(sizeof(float) * cells, 1024) +
+         align_up(sizeof(float) * B, 1024);
+}
+
+int rnnt_lattice_forward(const float* lp_blank, const float* lp_label, const int32_t* f_lens_host,
+                         const int32_t* y_lens_host, int B, int Tmax, int Umax, float* loss, float* c_blank,
+                         float* c_label, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 1 || Tmax < 1 || Umax < 0) return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d Umax=%d out of range", B, Tmax, Umax);
+  if (Umax + 1 > 1024) return fail(RNNT_ERR_UNSUPPORTED, "Umax+1=%d must be <= 1024", Umax + 1);
+  if (!lp_blank || !lp_label || !loss || !c_blank || !c_label || !workspace)
+    return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+  int rc = check_lens(f_lens_host, y_lens_host, B, Tmax, Umax);
+  if (rc) return rc;
+  if (workspace_bytes < rnnt_lattice_workspace_bytes(B, Tmax, Umax))
+    return fail(RNNT_ERR_WORKSPACE_TOO_SMALL, "workspace %zu bytes < required %zu", workspace_bytes,
+                rnnt_lattice_workspace_bytes(B, Tmax, Umax));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  const int U1 = Umax + 1, D = Tmax + U1;
+  const size_t cells = static_cast<size_t>(B) * D * U1;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return base + r; };
+  int* d_fl = reinterpret_cast<int*>(take(sizeof(int) * B));
+  int* d_yl = reinterpret_cast<int*>(take(sizeof(int) * B));
+  float* lpb = reinterpret_cast<float*>(take(sizeof(float) * cells));
+  float* lpl = reinterpret_cast<float*>(take(sizeof(float) * cells));
+  float* al = reinterpret_cast<float*>(take(sizeof(float) * cells));
+  float* be = reinterpret_cast<float*>(take(sizeof(float) * cells));
+  float* c1 = reinterpret_cast<float*>(take(sizeof(float) * cells));
+  float* c2 = reinterpret_cast<float*>(take(sizeof(float) * cells));
+  float* lnpb = reinterpret_cast<float*>(take(sizeof(float) * B));
+  CUDA_TRY(cudaMemcpyAsync(d_fl, f_lens_host, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(d_yl, y_lens_host, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+  Lattice L{};
+  L.tile_prefix = nullptr; L.f_lens = d_fl; L.y_lens = d_yl; L.B = B; L.Tmax = Tmax; L.U1max = U1; L.D = D;
+  launch_nat_to_diag(L, lp_blank, lp_label, lpb, lpl, s);
+  launch_lattice_alpha_beta(L, lpb, lpl, al, be, loss, lnpb, s);
+  launch_lattice_coefs(L, lpb, lpl, al, be, loss, c1, c2, s);
+  launch_diag_to_nat(L, c1, c2, c_blank, c_label, s);
+  CUDA_TRY(cudaGetLastError());
+  return RNNT_OK;
+}
+
+int rnnt_greedy_joint_argmax(const void* f, const void* g, const void* W, const float* bias, const int32_t* t_idx,
+                             int32_t* out_k, int B, int Tmax, int V, int H, void* stream) {
+  if (B < 1 || Tmax < 1 || V < 1) return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d V=%d out of range", B, Tmax, V);
+  if (H < 8 || H % 8 != 0) return fail(RNNT_ERR_UNSUPPORTED, "H=%d must be a positive multiple of 8", H);
+  if (H > 8192) return fail(RNNT_ERR_UNSUPPORTED, "H=%d must be <= 8192", H);
+  if (!f || !g || !W || !t_idx || !out_k) return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+  launch_greedy_argmax(static_cast<const __nv_bfloat16*>(f), static_cast<const __nv_bfloat16*>(g),
+                       static_cast<const __nv_bfloat16*>(W), bias, t_idx, out_k, B, Tmax, V, H,
+                       static_cast<cudaStream_t>(stream));
+  CUDA_TRY(cudaGetLastError());
+  return RNNT_OK;
+}
+
+int rnnt_debug_copy_stats(const void* workspace, int B, int Tmax, int Umax, int V, int H, float* lp_blank,
+                          float* lp_label, float* c_blank, float* c_label, float* lnp_beta, void* stream) {
+  int rc = check_dims(B, Tmax, Umax, V, H);
+  if (rc) return rc;
+  const Plan p = make_plan(B, Tmax, Umax, V, H);
+  Ws w{static_cast<uint8_t*>(const_cast<void*>(workspace)), p};
+  const Lattice L = make_lattice(w);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (lp_blank && lp_label) launch_diag_to_nat(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl), lp_blank, lp_label, s);
+  if (c_blank && c_label) launch_diag_to_nat(L, w.at<float>(p.o_c1), w.at<float>(p.o_c2), c_blank, c_label, s);
+  if (lnp_beta) CUDA_TRY(cudaMemcpyAsync(lnp_beta, w.at<float>(p.o_lnpb), sizeof(float) * B, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaGetLastError());
+  return RNNT_OK;
+}
+
+}  // extern "C"

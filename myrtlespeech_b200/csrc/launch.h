@@ -1,0 +1,90 @@
+// Internal launch interface between the C-ABI (capi.cu) and the kernel translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace rnnt {
+
+// ---- lattice.cu -------------------------------------------------------------------------------
+// alpha and beta wavefronts (one CTA per utterance and direction), writes alpha/beta (diagonal
+// layout), loss[b] = -ln P(y|x) and lnp_beta[b] = beta[0,0] (consistency check).
+void launch_lattice_alpha_beta(const Lattice& L, const float* lpb, const float* lpl, float* alpha, float* beta,
+                               float* loss, float* lnp_beta, cudaStream_t s);
+// c1 (blank-arc occupancy) and c2 (label-arc occupancy) per cell, diagonal layout.
+void launch_lattice_coefs(const Lattice& L, const float* lpb, const float* lpl, const float* alpha,
+                          const float* beta, const float* loss, float* c1, float* c2, cudaStream_t s);
+
+void launch_nat_to_diag(const Lattice& L, const float* a_nat, const float* b_nat, float* a_diag, float* b_diag,
+                        cudaStream_t s);
+void launch_diag_to_nat(const Lattice& L, const float* a_diag, const float* b_diag, float* a_nat, float* b_nat,
+                        cudaStream_t s);
+
+// ---- joint.cu ---------------------------------------------------------------------------------
+struct JointDims {
+  int V, H;   // vocabulary (incl. blank), joint width
+  int Vp;     // dz slab pitch (V rounded up to 64)
+  int blank;
+  int Umax;   // label tensor pitch
+};
+
+// h[row,:] = bf16(tanh(f[b,t,:] + g[b,u,:])) for every row of tiles [tile0, tile0 + n_tiles); padded rows = 0.
+void launch_hgen(const Lattice& L, const __nv_bfloat16* f, const __nv_bfloat16* g, __nv_bfloat16* hslab, int tile0,
+                 int n_tiles, int H, cudaStream_t s);
+
+// Wt[h][v] = W[v][h] (pitch Vp, zero padded)
+void launch_transpose_w(const __nv_bfloat16* W, __nv_bfloat16* Wt, int V, int H, int Vp, cudaStream_t s);
+
+struct FwdArgs {
+  const float* bias;   // [V] or null
+  const int* y;        // [B][Umax]
+  float* lse_tile;     // [n_tiles_total * 128]
+  float* lpb;          // diagonal layout
+  float* lpl;          // diagonal layout
+};
+// logits tile = hslab . W^T (tcgen05), fused online log-softmax; keeps only lse, lp_blank, lp_label.
+void launch_joint_fwd(const Lattice& L, const JointDims& d, const CUtensorMap& tm_h, const CUtensorMap& tm_w,
+                      const FwdArgs& a, int tile0, int n_tiles, int nc, cudaStream_t s);
+
+struct DzArgs {
+  const float* bias;
+  const int* y;
+  const float* lse_tile;
+  const float* lpb;
+  const float* lpl;
+  const float* c1;
+  const float* c2;
+  const float* grad_loss;  // [B]
+  float* db;               // [V] accumulated with red.add
+};
+// Recomputes the logits tile and writes dz = dL/dlogits (bf16) into the dz slab; accumulates db.
+void launch_joint_dz(const Lattice& L, const JointDims& d, const CUtensorMap& tm_h, const CUtensorMap& tm_w,
+                     const CUtensorMap& tm_dz_store, const DzArgs& a, int tile0, int n_tiles, int nc,
+                     cudaStream_t s);
+
+struct DhArgs {
+  const __nv_bfloat16* hslab;
+  float* df;  // [B][Tmax][H]
+  float* dg;  // [B][U1max][H]
+};
+// dh = dz . W (tcgen05, A = dz slab, B = W^T), dpre = dh * (1 - h^2), tile-reduced into df / dg.
+void launch_joint_dh(const Lattice& L, const JointDims& d, const CUtensorMap& tm_dz, const CUtensorMap& tm_wt,
+                     const DhArgs& a, int tile0, int n_tiles, int nc, cudaStream_t s);
+
+// dW += dz^T . h over the slab rows (tcgen05, both operands MN-major), split-K across CTAs, red.add into dW.
+void launch_joint_dw(const JointDims& d, const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, float* dW,
+                     int n_tiles, int n_ctas, int desc_mode, cudaStream_t s);
+
+// Greedy decode step: for each active utterance, k = argmax_v W . tanh(f[b,t_b,:] + g[b,:]) + bias.
+void launch_greedy_argmax(const __nv_bfloat16* f, const __nv_bfloat16* g, const __nv_bfloat16* W, const float* bias,
+                          const int* t_idx, int* out_k, int B, int Tmax, int V, int H, cudaStream_t s);
+
+int smem_bytes_fwd(int nc_total);
+int smem_bytes_dz(int nc_total);
+int smem_bytes_dh();
+int smem_bytes_dw();
+
+}  // namespace rnnt

@@ -1,0 +1,144 @@
+"""Autograd-level entry points over the C-ABI library (no torch types cross the boundary)."""
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _host_i32(x) -> torch.Tensor:
+    """Lengths as a contiguous host int32 tensor (they originate on the host in the reference,
+    data/batch.py:103-105; a device tensor costs one sync here)."""
+    if isinstance(x, torch.Tensor):
+        return x.detach().to(device="cpu", dtype=torch.int32).contiguous()
+    return torch.tensor(list(x), dtype=torch.int32)
+
+
+class _FusedJointLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, g, W, bias, y, f_lens, y_lens, blank):
+        lib = _lib.load()
+        if not f.is_cuda:
+            raise _lib.RNNTLibraryError("rnnt fused joint+loss needs CUDA tensors; there is no CPU fallback")
+        B, Tmax, H = f.shape
+        U1 = g.shape[1]
+        Umax = U1 - 1
+        V = W.shape[0]
+        fb = f.detach().to(torch.bfloat16).contiguous()
+        gb = g.detach().to(torch.bfloat16).contiguous()
+        Wb = W.detach().to(torch.bfloat16).contiguous()
+        bf = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        yi = y.detach().to(device=f.device, dtype=torch.int32).contiguous()
+        if yi.dim() != 2 or yi.shape[0] != B or (Umax > 0 and yi.shape[1] != Umax):
+            raise ValueError(f"targets must have shape ({B}, {Umax}), got {tuple(yi.shape)}")
+        fl, yl = _host_i32(f_lens), _host_i32(y_lens)
+        if fl.numel() != B or yl.numel() != B:
+            raise ValueError(f"length tensors must have {B} entries")
+        nbytes = lib.rnnt_fused_workspace_bytes(B, Tmax, Umax, V, H)
+        if nbytes == 0:
+            raise ValueError(lib.rnnt_last_error().decode())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=f.device)
+        loss = torch.empty(B, dtype=torch.float32, device=f.device)
+        _lib.check(lib.rnnt_fused_forward(_ptr(fb), _ptr(gb), _ptr(Wb), _ptr(bf), _ptr(yi), _ptr(fl), _ptr(yl),
+                                          B, Tmax, Umax, V, H, int(blank), _ptr(loss), _ptr(ws), nbytes, _stream()))
+        ctx.saved = (fb, gb, Wb, bf, yi, fl, yl, ws, nbytes)
+        ctx.dims = (B, Tmax, Umax, V, H, int(blank))
+        ctx.in_dtypes = (f.dtype, g.dtype, W.dtype, None if bias is None else bias.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lib = _lib.load()
+        fb, gb, Wb, bf, yi, fl, yl, ws, nbytes = ctx.saved
+        B, Tmax, Umax, V, H, blank = ctx.dims
+        dev = fb.device
+        gl = grad_loss.detach().to(torch.float32).contiguous()
+        df = torch.empty(B, Tmax, H, dtype=torch.float32, device=dev)
+        dg = torch.empty(B, Umax + 1, H, dtype=torch.float32, device=dev)
+        dW = torch.empty(V, H, dtype=torch.float32, device=dev)
+        db = torch.empty(V, dtype=torch.float32, device=dev)
+        _lib.check(lib.rnnt_fused_backward(_ptr(fb), _ptr(gb), _ptr(Wb), _ptr(bf), _ptr(yi), _ptr(fl), _ptr(yl),
+                                           B, Tmax, Umax, V, H, blank, _ptr(gl), _ptr(df), _ptr(dg), _ptr(dW),
+                                           _ptr(db), _ptr(ws), nbytes, _stream()))
+        tf, tg, tW, tb = ctx.in_dtypes
+        return (df.to(tf), dg.to(tg), dW.to(tW), None if tb is None else db.to(tb), None, None, None, None)
+
+
+def rnnt_joint_loss(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor],
+                    y: torch.Tensor, f_lens, y_lens, blank: int) -> torch.Tensor:
+    """Per-utterance ``-ln P(y|x)`` of the additive-tanh joint, fused with its lattice.
+
+    f (B,T,H), g (B,U+1,H), W (V,H), bias (V) or None, y (B,U) int; returns (B,) fp32.
+    The (B,T,U+1,V) logits are never materialised.
+    """
+    return _FusedJointLoss.apply(f, g, W, bias, y, f_lens, y_lens, blank)
+
+
+class _LatticeLoss(torch.autograd.Function):
+    """RNNTLoss on an explicit (B,T,U+1,V) logits tensor: torch does the log-softmax/gather plumbing,
+    the alpha/beta lattice runs in the CUDA library."""
+
+    @staticmethod
+    def forward(ctx, logits, y, f_lens, y_lens, blank):
+        lib = _lib.load()
+        if not logits.is_cuda:
+            raise _lib.RNNTLibraryError("rnnt lattice loss needs CUDA tensors; there is no CPU fallback")
+        B, Tmax, U1, V = logits.shape
+        Umax = U1 - 1
+        lp = torch.log_softmax(logits.detach().float(), dim=-1)
+        yi = y.detach().to(device=logits.device, dtype=torch.int64)
+        lpb = lp[..., blank].contiguous()
+        lpl = torch.zeros(B, Tmax, U1, dtype=torch.float32, device=logits.device)
+        if Umax > 0:
+            idx = yi[:, None, :, None].expand(B, Tmax, Umax, 1)
+            lpl[:, :, :Umax] = lp[:, :, :Umax].gather(-1, idx).squeeze(-1)
+        fl, yl = _host_i32(f_lens), _host_i32(y_lens)
+        nbytes = lib.rnnt_lattice_workspace_bytes(B, Tmax, Umax)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=logits.device)
+        loss = torch.empty(B, dtype=torch.float32, device=logits.device)
+        c1 = torch.empty(B, Tmax, U1, dtype=torch.float32, device=logits.device)
+        c2 = torch.empty_like(c1)
+        _lib.check(lib.rnnt_lattice_forward(_ptr(lpb), _ptr(lpl), _ptr(fl), _ptr(yl), B, Tmax, Umax, _ptr(loss),
+                                            _ptr(c1), _ptr(c2), _ptr(ws), nbytes, _stream()))
+        ctx.save_for_backward(lp, c1, c2, yi)
+        ctx.blank = blank
+        ctx.in_dtype = logits.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lp, c1, c2, yi = ctx.saved_tensors
+        B, Tmax, U1, V = lp.shape
+        Umax = U1 - 1
+        dz = torch.exp(lp) * (c1 + c2)[..., None]
+        dz[..., ctx.blank] -= c1
+        if Umax > 0:
+            idx = yi[:, None, :, None].expand(B, Tmax, Umax, 1)
+            dz[:, :, :Umax].scatter_add_(-1, idx, -c2[:, :, :Umax, None])
+        dz = dz * grad_loss.float()[:, None, None, None]
+        return dz.to(ctx.in_dtype), None, None, None, None
+
+
+def rnnt_loss_from_logits(logits, y, f_lens, y_lens, blank: int) -> torch.Tensor:
+    return _LatticeLoss.apply(logits, y, f_lens, y_lens, blank)
+
+
+def greedy_joint_argmax(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor],
+                        t_idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b] = argmax_v joint(f[b, t_idx[b]], g[b]); -1 where t_idx[b] < 0.  All bf16/int32 CUDA tensors."""
+    lib = _lib.load()
+    B, Tmax, H = f.shape
+    V = W.shape[0]
+    if out is None:
+        out = torch.empty(B, dtype=torch.int32, device=f.device)
+    _lib.check(lib.rnnt_greedy_joint_argmax(_ptr(f), _ptr(g), _ptr(W), _ptr(bias), _ptr(t_idx), _ptr(out),
+                                            B, Tmax, V, H, _stream()))
+    return out
