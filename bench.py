@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Headline benchmark: RNN-T joint + RNNTLoss forward + backward, utterances/s (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload target|c2|c3] [--impl ours|reference]
+
+One "step" = one pass of the hot path (joint -> log-softmax -> alpha/beta -> gradients df, dg, dW, db)
+over one batch of synthetic utterances.  N > 1 is launched by torchrun, one rank per GPU; utterances are
+sharded by rank (weak scaling: B per GPU fixed) and the only exchange is one NCCL all-reduce of the flat
+fp32 buffer [dW | db | loss_sum | n] per step.
+
+Printed JSON (rank 0): see the task contract.  `value` times the hot path with inputs resident in HBM;
+`e2e` times the public module API (RNNTJoint -> RNNTLoss.forward -> backward) with pinned HOST inputs, so
+the host->device copies and the device->host read of the loss are inside the timed region.
+`roofline` is for the dominant kernel class, from CUDA events bracketing each of its launches in one extra
+pass; `cpu_baseline` times the CPU stand-in for the reference path (oracle/cpu_path.py) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, T, U, V, H, description)
+    "target": (32, 500, 100, 1024, 1024, "north_star target / configs[3] per GPU: B=32 T=500 U=100 V=1024 H=1024 bf16"),
+    "c3": (32, 400, 150, 1024, 1024, "configs[2] subword: B=32 T=400 U=150 V=1024 H=1024 bf16"),
+    "c2": (32, 500, 100, 29, 512, "configs[1] chars: B=32 T=500 U=100 V=29 H=512 bf16"),
+}
+METRIC = "rnnt_joint_loss_fwd_bwd_utterances_per_s"
+KCLASSES = ["hgen", "joint_fwd", "joint_dz", "joint_dh", "joint_dw", "lattice", "coefs", "misc"]
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(tflops_burst=p["bf16_tflops"], tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm_gbs=p["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        # median over the busier half of the samples (the idle tail before/after is not "under load")
+        sm_sorted = sorted(sm, key=lambda x: -x)
+        under = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] if power else sm
+        return dict(sm_mhz=statistics.median(under) if under else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+
+
+def synth(B, T, U, V, H, seed, device):
+    """f,g ~ N(0,1), W,bias ~ U(-1/sqrt(H), 1/sqrt(H)), rounded to bf16 once; y uniform non-blank."""
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    f = torch.randn(B, T, H, generator=gen).bfloat16()
+    g = torch.randn(B, U + 1, H, generator=gen).bfloat16()
+    W = ((torch.rand(V, H, generator=gen) * 2 - 1) / H ** 0.5).bfloat16()
+    bias = (torch.rand(V, generator=gen) * 2 - 1) / H ** 0.5
+    y = torch.randint(0, V - 1, (B, U), generator=gen, dtype=torch.int32)
+    fl = torch.full((B,), T, dtype=torch.int32)
+    yl = torch.full((B,), U, dtype=torch.int32)
+    return f, g, W, bias, y, fl, yl
+
+
+def run_reference(args, B, T, U, V, H, desc, rank):
+    """--impl reference: the CPU stand-in for the reference path (oracle/cpu_path.py), all host threads,
+    each step a bounded sample (B_cpu utterances of the same T/U/V/H)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import cpu_path
+    b_cpu = 1 if V * H >= 1 << 18 else 4
+    r = cpu_path.time_steps(b_cpu, T, U, V, H, steps=args.steps, warmup=args.warmup)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": r["utt_per_s"], "unit": "utterances/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "sample_batch": b_cpu, "note": "reference snapshot has no RNN-T code; "
+                   "torch eager joint + torchaudio.functional.rnnt_loss on host cores stands in (oracle/cpu_path.py)"},
+        "cpu_baseline": {"value": r["utt_per_s"], "unit": "utterances/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["utt_per_s"], "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    B, T, U, V, H, desc = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        args.steps = 1 if args.steps is None else min(args.steps, 3)
+        args.warmup = 0 if args.warmup is None else min(args.warmup, 1)
+        run_reference(args, B, T, U, V, H, desc, rank)
+        return
+
+    args.steps = 20 if args.steps is None else args.steps
+    args.warmup = 5 if args.warmup is None else max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import ctypes
+    import myrtlespeech_b200 as M
+    from myrtlespeech_b200 import _lib
+    from myrtlespeech_b200.loss import RNNTLoss
+    from myrtlespeech_b200.model import RNNTJoint
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    f, g, W, bias, y, fl, yl = synth(B, T, U, V, H, 1234 + rank, dev)
+    blank = V - 1
+    fd, gd, yd = f.to(dev), g.to(dev), y.to(dev)
+    Wd = W.to(dev).requires_grad_(True)
+    bd = bias.to(dev).requires_grad_(True)
+    fd.requires_grad_(True); gd.requires_grad_(True)
+    flat = torch.zeros(V * H + V + 2, dtype=torch.float32, device=dev)  # [dW | db | loss_sum | n]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def hot_step():
+        loss = M.rnnt_joint_loss(fd, gd, Wd, bd, yd, fl, yl, blank)
+        total = loss.sum()
+        total.backward()
+        if world > 1:
+            flat[: V * H].copy_(Wd.grad.reshape(-1)); flat[V * H: V * H + V].copy_(bd.grad)
+            flat[V * H + V] = total.detach(); flat[V * H + V + 1] = float(B)
+            dist.all_reduce(flat)
+        fd.grad = gd.grad = Wd.grad = bd.grad = None
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """Per-step CUDA events on the launch stream; L2 flushed between steps outside the events."""
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    for _ in range(args.warmup):
+        hot_step()
+    barrier()
+    lib.rnnt_debug_set(b"reset_launches", 0)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(hot_step, args.steps)
+    launches = int(lib.rnnt_debug_get(b"launches"))
+    barrier()
+
+    # ---- end to end through the module API with host buffers -------------------------------------
+    joint = RNNTJoint(H, V)
+    with torch.no_grad():
+        joint.fc.weight.copy_(W.float()); joint.fc.bias.copy_(bias)
+    loss_mod = RNNTLoss(blank=blank, reduction="sum")
+    f_pin, g_pin, y_pin = f.pin_memory(), g.pin_memory(), y.pin_memory()
+    f_dev = torch.empty_like(fd); g_dev = torch.empty_like(gd); y_dev = torch.empty_like(yd)
+
+    def e2e_step():
+        f_dev.copy_(f_pin, non_blocking=True); g_dev.copy_(g_pin, non_blocking=True); y_dev.copy_(y_pin, non_blocking=True)
+        fx = f_dev.detach().requires_grad_(True); gx = g_dev.detach().requires_grad_(True)
+        out = joint((fx, fl), (gx, yl + 1))
+        loss = loss_mod(out, (y_dev, yl))
+        loss.backward()
+        if world > 1:
+            flat[: V * H].copy_(joint.fc.weight.grad.reshape(-1)); flat[V * H: V * H + V].copy_(joint.fc.bias.grad)
+            flat[V * H + V] = loss.detach(); flat[V * H + V + 1] = float(B)
+            dist.all_reduce(flat)
+        joint.zero_grad(set_to_none=True)
+        return float(loss.item())  # device -> host read of the step's result
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_ms = timed(e2e_step, args.steps)
+    barrier()
+    if rank == 0:
+        clocks = sampler.stop()
+
+    # ---- per-kernel-class times for the roofline (one extra pass, events around every launch) ----
+    lib.rnnt_debug_set(b"time_kernels", 1)
+    flush.zero_()
+    hot_step()
+    kms = (ctypes.c_double * 8)(); kn = (ctypes.c_longlong * 8)()
+    _lib.check(lib.rnnt_debug_kernel_times(kms, kn, 8))
+    lib.rnnt_debug_set(b"time_kernels", 0)
+
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = t.tolist()
+
+    if rank == 0:
+        n_rows = B * T * (U + 1)
+        flops = {"joint_fwd": 2.0 * n_rows * H * V, "joint_dz": 2.0 * n_rows * H * V, "joint_dh": 2.0 * n_rows * H * V,
+                 "joint_dw": 2.0 * n_rows * H * V}
+        kernels = {}
+        for i, name in enumerate(KCLASSES):
+            if kn[i]:
+                kernels[name] = {"launches": int(kn[i]), "ms_per_step": round(kms[i], 4)}
+                if name in flops:
+                    kernels[name]["tflops"] = round(flops[name] / (kms[i] * 1e-3) / 1e12, 1)
+        tensor_bound = V * H >= 1 << 18
+        if tensor_bound:
+            dom = max(flops, key=lambda k: kernels.get(k, {}).get("ms_per_step", 0.0))
+            achieved = kernels[dom]["tflops"]
+            roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops_sustained"],
+                        "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4),
+                        "frac_of_burst": round(achieved / peaks["tflops_burst"], 4), "traffic": None,
+                        "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                        "algorithmic_flops_per_launch": flops[dom] / kernels[dom]["launches"]}
+        else:
+            # V=29: the path is bound by the tanh/exp special-function work and the lattice scalars, not tensor
+            # cores; report HBM traffic of the per-cell lattice arrays (32 B/row) over lattice time
+            lat_ms = kernels.get("lattice", {}).get("ms_per_step", 0.0) + kernels.get("coefs", {}).get("ms_per_step", 0.0)
+            achieved = 32.0 * n_rows / (lat_ms * 1e-3) / 1e9 if lat_ms else 0.0
+            roofline = {"bound": "hbm", "kernel": "lattice+coefs", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None,
+                        "peak_source": peaks["source"], "note": "latency-bound by construction (T+U-1 dependent steps)"}
+        step_tflops = 6.0 * n_rows * H * V * world / (ms_total / args.steps * 1e-3) / 1e12
+
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import cpu_path
+            b_cpu = 1 if tensor_bound else 4
+            r = cpu_path.time_steps(b_cpu, T, U, V, H, steps=1, warmup=0)
+            cpu = {"value": round(r["utt_per_s"], 4), "unit": "utterances/s", "cores": r["cores"], "kind": "port",
+                   "sample": r["sample"]}
+
+        h2d = f.numel() * 2 + g.numel() * 2 + y.numel() * 4
+        out = {
+            "metric": METRIC, "value": round(B * world * args.steps / (ms_total * 1e-3), 2), "unit": "utterances/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "B_per_gpu": B, "global_batch": B * world, "T": T, "U": U, "V": V, "H": H,
+                       "parallelism": f"utterance-sharded dp{world}, one all-reduce of [dW|db|loss|n]",
+                       "l2": "flushed between timed steps (256 MiB write outside the per-step events)",
+                       "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks"},
+            "algorithmic_tflops": round(step_tflops, 1),
+            "frac_of_bf16_peak": {"burst": round(step_tflops / world / peaks["tflops_burst"], 4),
+                                  "sustained": round(step_tflops / world / peaks["tflops_sustained"], 4),
+                                  "basis": "6*N*H*V algorithmic flops per step (recompute not counted)"},
+            "e2e": {"value": round(B * world * args.steps / (e2e_ms * 1e-3), 2), "unit": "utterances/s",
+                    "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "api": "RNNTJoint -> RNNTLoss.forward(inputs, targets) -> backward, pinned host f/g/y"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

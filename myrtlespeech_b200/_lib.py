@@ -27,6 +27,8 @@ SIGNATURES = {
     "rnnt_greedy_joint_argmax": (_c_int, [_vp] * 6 + [_c_int] * 4 + [_vp]),
     "rnnt_debug_copy_stats": (_c_int, [_vp] + [_c_int] * 5 + [_vp] * 5 + [_vp]),
     "rnnt_debug_set": (None, [ctypes.c_char_p, _c_int]),
+    "rnnt_debug_get": (ctypes.c_longlong, [ctypes.c_char_p]),
+    "rnnt_debug_kernel_times": (_c_int, [_vp, _vp, _c_int]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <utility>
 #include <vector>
 
 #include "../../include/rnnt_b200.h"
@@ -21,7 +22,6 @@ namespace {
 using namespace rnnt;
 
 thread_local char g_err[512] = "";
-int g_dw_desc_mode = 0;
 int g_slab_tiles_override = 0;
 
 int fail(int code, const char* fmt, ...) {
@@ -39,6 +39,35 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- launch accounting (rnnt_debug_get / rnnt_debug_kernel_times) ---------------------------------
+enum KClass { K_HGEN = 0, K_FWD, K_DZ, K_DH, K_DW, K_LATTICE, K_COEFS, K_MISC, K_NCLASS };
+long long g_launches[K_NCLASS] = {0};
+bool g_time_kernels = false;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_pairs[K_NCLASS];
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t pool_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// Wraps one kernel launch: counts it and, in timing mode, brackets it with events on the launch stream.
+#define KLAUNCH(cls, stream, call)                                    \
+  do {                                                                \
+    ++g_launches[cls];                                                \
+    if (g_time_kernels) {                                             \
+      cudaEvent_t e0_ = pool_event(), e1_ = pool_event();             \
+      cudaEventRecord(e0_, stream);                                   \
+      call;                                                           \
+      cudaEventRecord(e1_, stream);                                   \
+      g_pairs[cls].push_back({e0_, e1_});                             \
+    } else {                                                          \
+      call;                                                           \
+    }                                                                 \
+  } while (0)
 
 int sm_count() {
   static int n = 0;
@@ -184,8 +213,38 @@ int rnnt_abi_version(void) { return 1; }
 const char* rnnt_last_error(void) { return g_err; }
 
 void rnnt_debug_set(const char* key, int value) {
-  if (!strcmp(key, "dw_desc_mode")) g_dw_desc_mode = value;
   if (!strcmp(key, "slab_tiles")) g_slab_tiles_override = value;
+  if (!strcmp(key, "time_kernels")) g_time_kernels = value != 0;
+  if (!strcmp(key, "reset_launches")) for (int i = 0; i < K_NCLASS; ++i) g_launches[i] = 0;
+}
+
+long long rnnt_debug_get(const char* key) {
+  if (!strcmp(key, "launches")) {
+    long long n = 0;
+    for (int i = 0; i < K_NCLASS; ++i) n += g_launches[i];
+    return n;
+  }
+  if (!strcmp(key, "n_classes")) return K_NCLASS;
+  return -1;
+}
+
+int rnnt_debug_kernel_times(double* ms, long long* count, int n) {
+  if (n < K_NCLASS) return fail(RNNT_ERR_INVALID_ARGUMENT, "need room for %d classes", (int)K_NCLASS);
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int c = 0; c < K_NCLASS; ++c) {
+    double t = 0.0;
+    for (auto& pr : g_pairs[c]) {
+      float m = 0.0f;
+      cudaEventElapsedTime(&m, pr.first, pr.second);
+      t += m;
+      g_event_pool.push_back(pr.first);
+      g_event_pool.push_back(pr.second);
+    }
+    ms[c] = t;
+    count[c] = static_cast<long long>(g_pairs[c].size());
+    g_pairs[c].clear();
+  }
+  return RNNT_OK;
 }
 
 size_t rnnt_fused_workspace_bytes(int B, int Tmax, int Umax, int V, int H) {
@@ -223,14 +282,15 @@ int rnnt_fused_forward(const void* f, const void* g, const void* W, const float*
   FwdArgs a{bias, y, w.at<float>(p.o_lse), w.at<float>(p.o_lpb), w.at<float>(p.o_lpl)};
   for (int t0 = 0; t0 < n_tiles; t0 += p.slab_tiles) {
     const int nt = (n_tiles - t0 < p.slab_tiles) ? n_tiles - t0 : p.slab_tiles;
-    launch_hgen(L, static_cast<const __nv_bfloat16*>(f), static_cast<const __nv_bfloat16*>(g),
-                w.at<__nv_bfloat16>(p.o_h), t0, nt, H, s);
-    launch_joint_fwd(L, d, tm_h, tm_w, a, t0, nt, nc, s);
+    KLAUNCH(K_HGEN, s, launch_hgen(L, static_cast<const __nv_bfloat16*>(f), static_cast<const __nv_bfloat16*>(g),
+                                   w.at<__nv_bfloat16>(p.o_h), t0, nt, H, s));
+    KLAUNCH(K_FWD, s, launch_joint_fwd(L, d, tm_h, tm_w, a, t0, nt, nc, s));
   }
-  launch_lattice_alpha_beta(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl), w.at<float>(p.o_alpha),
-                            w.at<float>(p.o_beta), loss, w.at<float>(p.o_lnpb), s);
-  launch_lattice_coefs(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl), w.at<float>(p.o_alpha), w.at<float>(p.o_beta),
-                       loss, w.at<float>(p.o_c1), w.at<float>(p.o_c2), s);
+  KLAUNCH(K_LATTICE, s, launch_lattice_alpha_beta(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl),
+                                                  w.at<float>(p.o_alpha), w.at<float>(p.o_beta), loss,
+                                                  w.at<float>(p.o_lnpb), s));
+  KLAUNCH(K_COEFS, s, launch_lattice_coefs(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl), w.at<float>(p.o_alpha),
+                                           w.at<float>(p.o_beta), loss, w.at<float>(p.o_c1), w.at<float>(p.o_c2), s));
   CUDA_TRY(cudaGetLastError());
   return RNNT_OK;
 }
@@ -259,7 +319,7 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
   CUDA_TRY(cudaMemsetAsync(dg, 0, sizeof(float) * static_cast<size_t>(B) * (Umax + 1) * H, s));
   CUDA_TRY(cudaMemsetAsync(dW, 0, sizeof(float) * static_cast<size_t>(V) * H, s));
   CUDA_TRY(cudaMemsetAsync(db, 0, sizeof(float) * V, s));
-  launch_transpose_w(static_cast<const __nv_bfloat16*>(W), w.at<__nv_bfloat16>(p.o_wt), V, H, p.Vp, s);
+  KLAUNCH(K_MISC, s, launch_transpose_w(static_cast<const __nv_bfloat16*>(W), w.at<__nv_bfloat16>(p.o_wt), V, H, p.Vp, s));
 
   const int nc_v = chunk_cols(V), nc_h = chunk_cols(H);
   const uint64_t slab_rows = static_cast<uint64_t>(p.slab_tiles) * kTileRows;
@@ -277,11 +337,11 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
   const int n_sm = sm_count();
   for (int t0 = 0; t0 < n_tiles; t0 += p.slab_tiles) {
     const int nt = (n_tiles - t0 < p.slab_tiles) ? n_tiles - t0 : p.slab_tiles;
-    launch_hgen(L, static_cast<const __nv_bfloat16*>(f), static_cast<const __nv_bfloat16*>(g),
-                w.at<__nv_bfloat16>(p.o_h), t0, nt, H, s);
-    launch_joint_dz(L, d, tm_h, tm_w, tm_dz, za, t0, nt, nc_v, s);
-    launch_joint_dh(L, d, tm_dz, tm_wt, ha, t0, nt, nc_h, s);
-    launch_joint_dw(d, tm_dz_mn, tm_h_mn, dW, nt, n_sm, g_dw_desc_mode, s);
+    KLAUNCH(K_HGEN, s, launch_hgen(L, static_cast<const __nv_bfloat16*>(f), static_cast<const __nv_bfloat16*>(g),
+                                   w.at<__nv_bfloat16>(p.o_h), t0, nt, H, s));
+    KLAUNCH(K_DZ, s, launch_joint_dz(L, d, tm_h, tm_w, tm_dz, za, t0, nt, nc_v, s));
+    KLAUNCH(K_DH, s, launch_joint_dh(L, d, tm_dz, tm_wt, ha, t0, nt, nc_h, s));
+    KLAUNCH(K_DW, s, launch_joint_dw(d, tm_dz_mn, tm_h_mn, dW, nt, n_sm, s));
   }
   CUDA_TRY(cudaGetLastError());
   return RNNT_OK;
@@ -325,10 +385,10 @@ int rnnt_lattice_forward(const float* lp_blank, const float* lp_label, const int
   CUDA_TRY(cudaMemcpyAsync(d_yl, y_lens_host, sizeof(int) * B, cudaMemcpyHostToDevice, s));
   Lattice L{};
   L.tile_prefix = nullptr; L.f_lens = d_fl; L.y_lens = d_yl; L.B = B; L.Tmax = Tmax; L.U1max = U1; L.D = D;
-  launch_nat_to_diag(L, lp_blank, lp_label, lpb, lpl, s);
-  launch_lattice_alpha_beta(L, lpb, lpl, al, be, loss, lnpb, s);
-  launch_lattice_coefs(L, lpb, lpl, al, be, loss, c1, c2, s);
-  launch_diag_to_nat(L, c1, c2, c_blank, c_label, s);
+  KLAUNCH(K_MISC, s, launch_nat_to_diag(L, lp_blank, lp_label, lpb, lpl, s));
+  KLAUNCH(K_LATTICE, s, launch_lattice_alpha_beta(L, lpb, lpl, al, be, loss, lnpb, s));
+  KLAUNCH(K_COEFS, s, launch_lattice_coefs(L, lpb, lpl, al, be, loss, c1, c2, s));
+  KLAUNCH(K_MISC, s, launch_diag_to_nat(L, c1, c2, c_blank, c_label, s));
   CUDA_TRY(cudaGetLastError());
   return RNNT_OK;
 }
@@ -339,9 +399,10 @@ int rnnt_greedy_joint_argmax(const void* f, const void* g, const void* W, const 
   if (H < 8 || H % 8 != 0) return fail(RNNT_ERR_UNSUPPORTED, "H=%d must be a positive multiple of 8", H);
   if (H > 8192) return fail(RNNT_ERR_UNSUPPORTED, "H=%d must be <= 8192", H);
   if (!f || !g || !W || !t_idx || !out_k) return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
-  launch_greedy_argmax(static_cast<const __nv_bfloat16*>(f), static_cast<const __nv_bfloat16*>(g),
-                       static_cast<const __nv_bfloat16*>(W), bias, t_idx, out_k, B, Tmax, V, H,
-                       static_cast<cudaStream_t>(stream));
+  KLAUNCH(K_MISC, static_cast<cudaStream_t>(stream),
+          launch_greedy_argmax(static_cast<const __nv_bfloat16*>(f), static_cast<const __nv_bfloat16*>(g),
+                               static_cast<const __nv_bfloat16*>(W), bias, t_idx, out_k, B, Tmax, V, H,
+                               static_cast<cudaStream_t>(stream)));
   CUDA_TRY(cudaGetLastError());
   return RNNT_OK;
 }

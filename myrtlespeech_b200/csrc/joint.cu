@@ -429,7 +429,6 @@ struct DwArgs {
   int nkb;          // k-blocks (64 slab rows) in this slab
   int per_cta;      // work items (tile, k-block) per CTA
   int total;        // n_vt * n_ht * nkb
-  int desc_mode;    // debugging aid: 0 = canonical (lbo = box stride, sbo = 1024)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -484,8 +483,10 @@ dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(128, 256, true, true);
-    const uint32_t lbo = (p.desc_mode == 1) ? 1024u : static_cast<uint32_t>(kDwBox);
-    const uint32_t sbo = (p.desc_mode == 1) ? static_cast<uint32_t>(kDwBox) : 1024u;
+    // MN-major SW128 (verified on hardware): lbo = distance between 64-element M/N groups (one TMA box),
+    // sbo = distance between 8-row k groups
+    const uint32_t lbo = static_cast<uint32_t>(kDwBox);
+    const uint32_t sbo = 1024u;
     int it = 0, run = 0;
     int item = begin;
     while (item < end) {
@@ -730,7 +731,7 @@ void launch_joint_dh(const Lattice& L, const JointDims& d, const CUtensorMap& tm
 }
 
 void launch_joint_dw(const JointDims& d, const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, float* dW,
-                     int n_tiles, int n_ctas, int desc_mode, cudaStream_t s) {
+                     int n_tiles, int n_ctas, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem);
@@ -744,7 +745,6 @@ void launch_joint_dw(const JointDims& d, const CUtensorMap& tm_dz_mn, const CUte
   if (n_ctas > a.total) n_ctas = a.total;
   a.per_cta = (a.total + n_ctas - 1) / n_ctas;
   const int grid = (a.total + a.per_cta - 1) / a.per_cta;
-  a.desc_mode = desc_mode;
   dw_kernel<<<grid, kThreads, kDwSmem, s>>>(tm_dz_mn, tm_h_mn, a);
 }
 

@@ -76,7 +76,7 @@ void launch_joint_dh(const Lattice& L, const JointDims& d, const CUtensorMap& tm
 
 // dW += dz^T . h over the slab rows (tcgen05, both operands MN-major), split-K across CTAs, red.add into dW.
 void launch_joint_dw(const JointDims& d, const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, float* dW,
-                     int n_tiles, int n_ctas, int desc_mode, cudaStream_t s);
+                     int n_tiles, int n_ctas, cudaStream_t s);
 
 // Greedy decode step: for each active utterance, k = argmax_v W . tanh(f[b,t_b,:] + g[b,:]) + bias.
 void launch_greedy_argmax(const __nv_bfloat16* f, const __nv_bfloat16* g, const __nv_bfloat16* W, const float* bias,
