@@ -97,6 +97,7 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
   p.max_tiles = B * ((Tmax + kTT - 1) / kTT) * ((p.U1 + kTU - 1) / kTU);
   p.slab_tiles = g_slab_tiles_override > 0 ? g_slab_tiles_override : 148;
   if (p.slab_tiles > p.max_tiles) p.slab_tiles = p.max_tiles;
+  p.slab_tiles = (p.slab_tiles + 1) / 2 * 2;  // CTA pairs: a slab holds an even number of tiles
   const size_t cells = static_cast<size_t>(B) * p.D * p.U1;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
@@ -176,12 +177,12 @@ struct Ws {
   template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
 };
 
-Lattice make_lattice(const Ws& w) {
+Lattice make_lattice(const Ws& w, int n_tiles_total) {
   Lattice L{};
   L.tile_prefix = w.at<int>(w.p.o_prefix);
   L.f_lens = w.at<int>(w.p.o_flens);
   L.y_lens = w.at<int>(w.p.o_ylens);
-  L.B = w.p.B; L.Tmax = w.p.Tmax; L.U1max = w.p.U1; L.D = w.p.D;
+  L.B = w.p.B; L.Tmax = w.p.Tmax; L.U1max = w.p.U1; L.D = w.p.D; L.n_tiles_total = n_tiles_total;
   return L;
 }
 
@@ -269,14 +270,14 @@ int rnnt_fused_forward(const void* f, const void* g, const void* W, const float*
   int n_tiles = 0;
   rc = upload_lengths(w, f_lens_host, y_lens_host, &n_tiles, s);
   if (rc) return rc;
-  const Lattice L = make_lattice(w);
+  const Lattice L = make_lattice(w, n_tiles);
   JointDims d{V, H, p.Vp, blank, Umax > 0 ? Umax : 1};
 
   const int nc = chunk_cols(V);
   CUtensorMap tm_h, tm_w;
   rc = make_map(&tm_h, w.at<void>(p.o_h), H, static_cast<uint64_t>(p.slab_tiles) * kTileRows, H, 64, 128);
   if (rc) return rc;
-  rc = make_map(&tm_w, W, H, V, H, 64, nc);
+  rc = make_map(&tm_w, W, H, V, H, 64, nc / 2);
   if (rc) return rc;
 
   FwdArgs a{bias, y, w.at<float>(p.o_lse), w.at<float>(p.o_lpb), w.at<float>(p.o_lpl)};
@@ -312,7 +313,7 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Ws w{static_cast<uint8_t*>(workspace), p};
   const int n_tiles = count_tiles(f_lens_host, y_lens_host, B);
-  const Lattice L = make_lattice(w);
+  const Lattice L = make_lattice(w, n_tiles);
   JointDims d{V, H, p.Vp, blank, Umax > 0 ? Umax : 1};
 
   CUDA_TRY(cudaMemsetAsync(df, 0, sizeof(float) * static_cast<size_t>(B) * Tmax * H, s));
@@ -325,9 +326,9 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
   const uint64_t slab_rows = static_cast<uint64_t>(p.slab_tiles) * kTileRows;
   CUtensorMap tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn;
   if ((rc = make_map(&tm_h, w.at<void>(p.o_h), H, slab_rows, H, 64, 128))) return rc;
-  if ((rc = make_map(&tm_w, W, H, V, H, 64, nc_v))) return rc;
+  if ((rc = make_map(&tm_w, W, H, V, H, 64, nc_v / 2))) return rc;
   if ((rc = make_map(&tm_dz, w.at<void>(p.o_dz), p.Vp, slab_rows, p.Vp, 64, 128))) return rc;
-  if ((rc = make_map(&tm_wt, w.at<void>(p.o_wt), p.Vp, H, p.Vp, 64, nc_h))) return rc;
+  if ((rc = make_map(&tm_wt, w.at<void>(p.o_wt), p.Vp, H, p.Vp, 64, nc_h / 2))) return rc;
   if ((rc = make_map(&tm_dz_mn, w.at<void>(p.o_dz), p.Vp, slab_rows, p.Vp, 64, 64))) return rc;
   if ((rc = make_map(&tm_h_mn, w.at<void>(p.o_h), H, slab_rows, H, 64, 64))) return rc;
 
@@ -413,7 +414,7 @@ int rnnt_debug_copy_stats(const void* workspace, int B, int Tmax, int Umax, int 
   if (rc) return rc;
   const Plan p = make_plan(B, Tmax, Umax, V, H);
   Ws w{static_cast<uint8_t*>(const_cast<void*>(workspace)), p};
-  const Lattice L = make_lattice(w);
+  const Lattice L = make_lattice(w, 0);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (lp_blank && lp_label) launch_diag_to_nat(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl), lp_blank, lp_label, s);
   if (c_blank && c_label) launch_diag_to_nat(L, w.at<float>(p.o_c1), w.at<float>(p.o_c2), c_blank, c_label, s);

@@ -26,6 +26,7 @@ struct Lattice {
   int Tmax;
   int U1max;  // Umax + 1
   int D;      // diagonals allocated per utterance (Tmax + U1max)
+  int n_tiles_total;  // tiles in the batch (== tile_prefix[B])
 };
 
 struct TileInfo {

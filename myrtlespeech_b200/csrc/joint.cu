@@ -27,8 +27,8 @@ namespace {
 constexpr int kBM = 128;                    // rows per tile == TMEM lanes
 constexpr int kBK = 64;                     // bf16 per k-block (one 128-byte swizzle row)
 constexpr int kNCmax = 256;                 // max columns per chunk (UMMA N)
-constexpr int kAStage = kBM * kBK * 2;      // 16 KB
-constexpr int kBStage = kNCmax * kBK * 2;   // 32 KB
+constexpr int kAStage = kBM * kBK * 2;            // 16 KB: this CTA's 128 rows
+constexpr int kBStage = (kNCmax / 2) * kBK * 2;   // 16 KB: this CTA's half of the chunk's N rows (CTA pair)
 constexpr int kStageBytes = kAStage + kBStage;
 constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
@@ -39,15 +39,16 @@ constexpr int kDhPitch = 65;                // fp32 pitch of the dpre transpose 
 enum Epi { kFwd = 0, kDz = 1, kDh = 2 };
 
 template <int EPI> struct Cfg;
-template <> struct Cfg<kFwd> { static constexpr int stages = 4; static constexpr int extra = kMaxBiasCols * 4; };
-template <> struct Cfg<kDz>  { static constexpr int stages = 3; static constexpr int extra = kMaxBiasCols * 4 + kBM * kNCmax * 2; };
-template <> struct Cfg<kDh>  { static constexpr int stages = 3; static constexpr int extra = kBM * kDhPitch * 4; };
+template <> struct Cfg<kFwd> { static constexpr int stages = 6; static constexpr int extra = kMaxBiasCols * 4; };
+template <> struct Cfg<kDz>  { static constexpr int stages = 4; static constexpr int extra = kMaxBiasCols * 4 + kBM * kNCmax * 2; };
+template <> struct Cfg<kDh>  { static constexpr int stages = 5; static constexpr int extra = kBM * kDhPitch * 4; };
 
 template <int EPI> constexpr int smem_total() { return Cfg<EPI>::stages * kStageBytes + Cfg<EPI>::extra + 1024 + 256; }
 
 struct GemmArgs {
   Lattice L;
   int tile0;      // first global tile handled by this launch; CTA x handles tile0 + x, slab rows [128x, 128x+128)
+  int n_tiles_total;  // tiles in the whole batch; a CTA whose tile is beyond it is the "ghost" half of an odd pair
   int n_total;    // valid N extent (V or H)
   int nc;         // columns per chunk, multiple of 32, <= 256
   int n_chunks;
@@ -99,27 +100,34 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x;
+  // CTA pair: the even CTA ("leader") issues every MMA for both (M = 256: 128 rows from each CTA's smem, each
+  // CTA supplies half of the chunk's N rows of B); accumulators land in each CTA's own TMEM.
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const bool ghost = (p.tile0 + m) >= p.n_tiles_total;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_a);
     prefetch_tmap(&tm_b);
     if (EPI == kDz) prefetch_tmap(&tm_out);
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     fence_barrier_init();
     *s_ti = decode_tile(p.L, p.tile0 + m);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    tmem_alloc_2cta(tmem_slot, kTmemCols);
+    tmem_relinquish_2cta();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const TileInfo ti = *s_ti;
 
-  const uint32_t b_bytes = static_cast<uint32_t>(p.nc) * kBK * 2;
+  const int nc_half = p.nc >> 1;
+  const uint32_t b_bytes = static_cast<uint32_t>(nc_half) * kBK * 2;
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -130,18 +138,19 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], kAStage + b_bytes);
+          // the leader's barrier collects the bytes of both CTAs' loads
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * (kAStage + b_bytes));
           uint8_t* sa = stage_base + s * kStageBytes;
-          tma_load_2d(sa, &tm_a, &full_bar[s], k * kBK, m * kBM);
-          tma_load_2d(sa + kAStage, &tm_b, &full_bar[s], k * kBK, j * p.nc);
+          tma_load_2d_pair(sa, &tm_a, &full_bar[s], k * kBK, m * kBM);
+          tma_load_2d_pair(sa + kAStage, &tm_b, &full_bar[s], k * kBK, j * p.nc + static_cast<int>(rank) * nc_half);
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------- MMA issuer ----------------------------------
-    const uint32_t idesc = make_idesc_bf16(kBM, p.nc, false, false);
+    // ------------------------------- MMA issuer (leader CTA only) -----------------
+    const uint32_t idesc = make_idesc_bf16(2 * kBM, p.nc, false, false);
     int it = 0;
-    for (int j = 0; j < p.n_chunks; ++j) {
+    for (int j = 0; leader && j < p.n_chunks; ++j) {
       const int buf = j & 1;
       mbar_wait(&tempty_bar[buf], ((j >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -158,10 +167,10 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           for (int kk = 0; kk < kBK / 16; ++kk) {
             const uint64_t ad = make_smem_desc_sw128(a_addr + kk * 32, 16, 1024);
             const uint64_t bd = make_smem_desc_sw128(b_addr + kk * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (k | kk) != 0 ? 1u : 0u);
+            umma_bf16_pair(d_tmem, ad, bd, idesc, (k | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
-          if (k == p.k_blocks - 1) umma_commit(&tfull_bar[buf]);
+          umma_commit_pair(&empty_bar[s], 3);                           // frees the slot in both CTAs
+          if (k == p.k_blocks - 1) umma_commit_pair(&tfull_bar[buf], 3);  // accumulator ready in both CTAs
         }
         __syncwarp();
       }
@@ -173,7 +182,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int et = (warp - 2) * 32 + lane;  // epilogue thread id 0..127
     const int dt = r >> 3, du = r & 7;
     const int t = ti.t0 + dt, u = ti.u0 + du;
-    const bool valid = (t < ti.T) && (u <= ti.U);
+    const bool valid = !ghost && (t < ti.T) && (u <= ti.U);
     const size_t grow = static_cast<size_t>(p.tile0 + m) * kBM + r;
     const size_t didx = valid ? diag_index(p.L, ti.b, t, u) : 0;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -224,10 +233,10 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          if (lane == 0) mbar_arrive_even_cta(&tempty_bar[buf]);
         }
         const float lse2 = mx + lg2f(sum);
-        p.lse_tile[grow] = valid ? lse2 * kLn2 : 0.0f;
+        if (!ghost) p.lse_tile[grow] = valid ? lse2 * kLn2 : 0.0f;
         if (valid) {
           p.lpb[didx] = (zb - lse2) * kLn2;
           p.lpl[didx] = (u < ti.U) ? (zl - lse2) * kLn2 : kNeg;
@@ -278,7 +287,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          if (lane == 0) mbar_arrive_even_cta(&tempty_bar[buf]);
           // exact values for the two special columns of this row (avoids a bf16 read-modify-write)
           {
             const int cb = p.blank - j * p.nc;
@@ -296,7 +305,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           fence_proxy_async_smem();
           named_bar_sync(1, kEpiThreads);
-          if (et == 0) {
+          if (et == 0 && !ghost) {
             for (int bx = 0; bx < n_box; ++bx) {
               const int col = j * p.nc + bx * 64;
               if (col < p.Vp) tma_store_2d(&tm_out, stage_out + bx * (kBM * 128), col, m * kBM);
@@ -306,7 +315,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           // db: column sums of the staged tile (thread et owns columns 2et, 2et+1 of the chunk)
           {
             const int cc = 2 * et;
-            if (cc < p.nc) {
+            if (cc < p.nc && !ghost) {
               float s0 = 0.0f, s1 = 0.0f;
               const uint8_t* colp = stage_out + (cc >> 6) * (kBM * 128) + (cc & 7) * 2;
               const int ch = (cc & 63) >> 3;
@@ -371,7 +380,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (sub == n_sub - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (lane == 0) mbar_arrive_even_cta(&tempty_bar[buf]);
           }
           named_bar_sync(1, kEpiThreads);
           const int col = j * p.nc + sub * 64 + rc;
@@ -404,30 +413,32 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer may still be reading this CTA's smem / signalling its barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// dW += dz^T . h  : M = V (128 per tile), N = H (256 per tile), K = slab rows (64 per k-block).
-// Both operands are read MN-major from the row-major slabs ([rows][Vp] and [rows][H]) as 128B-swizzled
-// TMA boxes of 64 elements x 64 rows.
+// dW += dz^T . h  : M = V (256 per CTA pair, 128 per CTA), N = H (256 per tile), K = slab rows (64 per k-block).
+// Both operands are read MN-major straight from the row-major slabs ([rows][Vp] and [rows][H]) as
+// 128B-swizzled TMA boxes of 64 elements x 64 rows.  Work items (output tile, k-block) are dealt out evenly
+// to the CTA pairs (split-K); each run of items on one output tile ends with a red.add flush into dW.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDwStages = 4;
+constexpr int kDwStages = 6;
 constexpr int kDwBox = 64 * 128;  // 8 KB: 64 rows x 128 B
-constexpr int kDwAStage = 2 * kDwBox;
-constexpr int kDwBStage = 4 * kDwBox;
+constexpr int kDwAStage = 2 * kDwBox;   // this CTA's 128 of the pair's 256 V rows
+constexpr int kDwBStage = 2 * kDwBox;   // this CTA's 128 of the tile's 256 H columns
 constexpr int kDwStageBytes = kDwAStage + kDwBStage;
 constexpr int kDwSmem = kDwStages * kDwStageBytes + 1024 + 256;
 
 struct DwArgs {
   float* dW;
   int V, H;
-  int n_vt, n_ht;   // output tiles along V (128) and H (256)
+  int n_vt, n_ht;   // output tiles along V (256 per pair) and H (256)
   int nkb;          // k-blocks (64 slab rows) in this slab
-  int per_cta;      // work items (tile, k-block) per CTA
+  int per_pair;     // work items (tile, k-block) per CTA pair
   int total;        // n_vt * n_ht * nkb
 };
 
@@ -444,22 +455,26 @@ dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int begin = blockIdx.x * p.per_cta;
-  const int end = min(begin + p.per_cta, p.total);
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int begin = pair * p.per_pair;
+  const int end = min(begin + p.per_pair, p.total);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_dz);
     prefetch_tmap(&tm_h);
     for (int i = 0; i < kDwStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    tmem_alloc_2cta(tmem_slot, kTmemCols);
+    tmem_relinquish_2cta();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -472,24 +487,26 @@ dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUt
         const int s = it % kDwStages;
         const uint32_t ph = (it / kDwStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], kDwStageBytes);
+        if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * kDwStageBytes);
         uint8_t* sa = smem + s * kDwStageBytes;
+        const int v0 = vm * 256 + static_cast<int>(rank) * 128;
+        const int h0 = hn * 256 + static_cast<int>(rank) * 128;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) tma_load_2d(sa + q * kDwBox, &tm_dz, &full_bar[s], vm * 128 + q * 64, kb * 64);
+        for (int q = 0; q < 2; ++q) tma_load_2d_pair(sa + q * kDwBox, &tm_dz, &full_bar[s], v0 + q * 64, kb * 64);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          tma_load_2d(sa + kDwAStage + q * kDwBox, &tm_h, &full_bar[s], hn * 256 + q * 64, kb * 64);
+        for (int q = 0; q < 2; ++q)
+          tma_load_2d_pair(sa + kDwAStage + q * kDwBox, &tm_h, &full_bar[s], h0 + q * 64, kb * 64);
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, 256, true, true);
+    const uint32_t idesc = make_idesc_bf16(256, 256, true, true);
     // MN-major SW128 (verified on hardware): lbo = distance between 64-element M/N groups (one TMA box),
     // sbo = distance between 8-row k groups
     const uint32_t lbo = static_cast<uint32_t>(kDwBox);
     const uint32_t sbo = 1024u;
     int it = 0, run = 0;
     int item = begin;
-    while (item < end) {
+    while (leader && item < end) {
       const int tile = item / p.nkb;
       const int run_end = min(end, (tile + 1) * p.nkb);
       const int buf = run & 1;
@@ -509,10 +526,10 @@ dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUt
           for (int kk = 0; kk < 4; ++kk) {  // 16 slab rows per MMA
             const uint64_t ad = make_smem_desc_sw128(a_addr + kk * 2048, lbo, sbo);
             const uint64_t bd = make_smem_desc_sw128(b_addr + kk * 2048, lbo, sbo);
-            umma_bf16(d_tmem, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+            umma_bf16_pair(d_tmem, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
           }
-          umma_commit(&empty_bar[s]);
-          if (item == run_end - 1) umma_commit(&tfull_bar[buf]);
+          umma_commit_pair(&empty_bar[s], 3);
+          if (item == run_end - 1) umma_commit_pair(&tfull_bar[buf], 3);
         }
         first = false;
         __syncwarp();
@@ -532,7 +549,7 @@ dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUt
       const int buf = run & 1;
       mbar_wait(&tfull_bar[buf], (run >> 1) & 1);
       tc_fence_after();
-      const int v = vm * 128 + r;
+      const int v = vm * 256 + static_cast<int>(rank) * 128 + r;
       float* out = p.dW + static_cast<size_t>(v) * p.H + hn * 256;
 #pragma unroll 1
       for (int g = 0; g < 8; ++g) {
@@ -556,7 +573,7 @@ dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) mbar_arrive_even_cta(&tempty_bar[buf]);
       item = run_end;
       ++run;
     }
@@ -564,9 +581,10 @@ dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
   }
 }
 
@@ -680,7 +698,16 @@ void launch_slab_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     cudaFuncSetAttribute(slab_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total<EPI>());
     configured = true;
   }
-  slab_gemm_kernel<EPI><<<n_tiles, kThreads, smem_total<EPI>(), s>>>(ta, tb, tout, a);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((n_tiles + 1) / 2 * 2);  // CTA pairs; an odd tail gets a ghost CTA
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_total<EPI>();
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, slab_gemm_kernel<EPI>, ta, tb, tout, a);
 }
 
 }  // namespace
@@ -703,7 +730,7 @@ void launch_transpose_w(const __nv_bfloat16* W, __nv_bfloat16* Wt, int V, int H,
 void launch_joint_fwd(const Lattice& L, const JointDims& d, const CUtensorMap& tm_h, const CUtensorMap& tm_w,
                       const FwdArgs& a, int tile0, int n_tiles, int nc, cudaStream_t s) {
   GemmArgs g{};
-  g.L = L; g.tile0 = tile0; g.n_total = d.V; g.nc = nc; g.n_chunks = (d.V + nc - 1) / nc;
+  g.L = L; g.tile0 = tile0; g.n_tiles_total = L.n_tiles_total; g.n_total = d.V; g.nc = nc; g.n_chunks = (d.V + nc - 1) / nc;
   g.k_blocks = (d.H + kBK - 1) / kBK; g.blank = d.blank; g.Umax = d.Umax; g.Vp = d.Vp; g.H = d.H;
   g.bias = a.bias; g.y = a.y; g.lse_tile = a.lse_tile; g.lpb = a.lpb; g.lpl = a.lpl;
   launch_slab_gemm<kFwd>(tm_h, tm_w, tm_h, g, n_tiles, s);
@@ -713,7 +740,7 @@ void launch_joint_dz(const Lattice& L, const JointDims& d, const CUtensorMap& tm
                      const CUtensorMap& tm_dz_store, const DzArgs& a, int tile0, int n_tiles, int nc,
                      cudaStream_t s) {
   GemmArgs g{};
-  g.L = L; g.tile0 = tile0; g.n_total = d.V; g.nc = nc; g.n_chunks = (d.V + nc - 1) / nc;
+  g.L = L; g.tile0 = tile0; g.n_tiles_total = L.n_tiles_total; g.n_total = d.V; g.nc = nc; g.n_chunks = (d.V + nc - 1) / nc;
   g.k_blocks = (d.H + kBK - 1) / kBK; g.blank = d.blank; g.Umax = d.Umax; g.Vp = d.Vp; g.H = d.H;
   g.bias = a.bias; g.y = a.y; g.lse_tile = const_cast<float*>(a.lse_tile);
   g.lpb = const_cast<float*>(a.lpb); g.lpl = const_cast<float*>(a.lpl);
@@ -724,7 +751,7 @@ void launch_joint_dz(const Lattice& L, const JointDims& d, const CUtensorMap& tm
 void launch_joint_dh(const Lattice& L, const JointDims& d, const CUtensorMap& tm_dz, const CUtensorMap& tm_wt,
                      const DhArgs& a, int tile0, int n_tiles, int nc, cudaStream_t s) {
   GemmArgs g{};
-  g.L = L; g.tile0 = tile0; g.n_total = d.H; g.nc = nc; g.n_chunks = (d.H + nc - 1) / nc;
+  g.L = L; g.tile0 = tile0; g.n_tiles_total = L.n_tiles_total; g.n_total = d.H; g.nc = nc; g.n_chunks = (d.H + nc - 1) / nc;
   g.k_blocks = (d.Vp + kBK - 1) / kBK; g.blank = d.blank; g.Umax = d.Umax; g.Vp = d.Vp; g.H = d.H;
   g.hslab = a.hslab; g.df = a.df; g.dg = a.dg;
   launch_slab_gemm<kDh>(tm_dz, tm_wt, tm_dz, g, n_tiles, s);
@@ -739,13 +766,24 @@ void launch_joint_dw(const JointDims& d, const CUtensorMap& tm_dz_mn, const CUte
   }
   DwArgs a{};
   a.dW = dW; a.V = d.V; a.H = d.H;
-  a.n_vt = (d.V + 127) / 128; a.n_ht = (d.H + 255) / 256;
+  a.n_vt = (d.V + 255) / 256; a.n_ht = (d.H + 255) / 256;
   a.nkb = n_tiles * 2;  // 128 rows per tile, 64 per k-block
   a.total = a.n_vt * a.n_ht * a.nkb;
-  if (n_ctas > a.total) n_ctas = a.total;
-  a.per_cta = (a.total + n_ctas - 1) / n_ctas;
-  const int grid = (a.total + a.per_cta - 1) / a.per_cta;
-  dw_kernel<<<grid, kThreads, kDwSmem, s>>>(tm_dz_mn, tm_h_mn, a);
+  int n_pairs = n_ctas / 2;
+  if (n_pairs < 1) n_pairs = 1;
+  if (n_pairs > a.total) n_pairs = a.total;
+  a.per_pair = (a.total + n_pairs - 1) / n_pairs;
+  n_pairs = (a.total + a.per_pair - 1) / a.per_pair;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * n_pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kDwSmem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, dw_kernel, tm_dz_mn, tm_h_mn, a);
 }
 
 void launch_greedy_argmax(const __nv_bfloat16* f, const __nv_bfloat16* g, const __nv_bfloat16* W, const float* bias,

@@ -114,6 +114,8 @@ class RNNTGreedyDecoder(torch.nn.Module):
 
 
 def _select_hidden(mask: torch.Tensor, new, old):
+    if new is None or old is None:  # stateless prediction network, or first step (old state is "zeros")
+        return new
     if isinstance(new, tuple):
         return tuple(_select_hidden(mask, n, o) for n, o in zip(new, old))
     return torch.where(mask[None, :, None], new, old)
