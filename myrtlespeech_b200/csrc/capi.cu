@@ -216,6 +216,7 @@ const char* rnnt_last_error(void) { return g_err; }
 void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "slab_tiles")) g_slab_tiles_override = value;
   if (!strcmp(key, "time_kernels")) g_time_kernels = value != 0;
+  if (!strcmp(key, "gemm_dbg")) set_gemm_dbg(value);
   if (!strcmp(key, "reset_launches")) for (int i = 0; i < K_NCLASS; ++i) g_launches[i] = 0;
 }
 

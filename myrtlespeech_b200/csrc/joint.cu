@@ -37,6 +37,7 @@ constexpr int kMaxBiasCols = 2048;          // V (rounded up to chunks) supporte
 constexpr int kDhPitch = 65;                // fp32 pitch of the dpre transpose tile
 
 enum Epi { kFwd = 0, kDz = 1, kDh = 2 };
+int g_gemm_dbg = 0;
 
 template <int EPI> struct Cfg;
 template <> struct Cfg<kFwd> { static constexpr int stages = 6; static constexpr int extra = kMaxBiasCols * 4; };
@@ -49,6 +50,7 @@ struct GemmArgs {
   Lattice L;
   int tile0;      // first global tile handled by this launch; CTA x handles tile0 + x, slab rows [128x, 128x+128)
   int n_tiles_total;  // tiles in the whole batch; a CTA whose tile is beyond it is the "ghost" half of an odd pair
+  int dbg;            // bring-up switches (0 in production): 1 = skip epilogue work, 2 = skip TMA after the first ring fill
   int n_total;    // valid N extent (V or H)
   int nc;         // columns per chunk, multiple of 32, <= 256
   int n_chunks;
@@ -138,6 +140,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if ((p.dbg & 2) && it >= kStages) { if (leader) mbar_arrive(&full_bar[s]); continue; }
           // the leader's barrier collects the bytes of both CTAs' loads
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * (kAStage + b_bytes));
           uint8_t* sa = stage_base + s * kStageBytes;
@@ -205,7 +208,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const int buf = j & 1;
           mbar_wait(&tfull_bar[buf], (j >> 1) & 1);
           tc_fence_after();
-          for (int g = 0; g < p.nc / 32; ++g) {
+          for (int g = 0; g < ((p.dbg & 1) ? 0 : p.nc / 32); ++g) {
             uint32_t raw[32];
             tmem_ld32(lane_taddr + buf * kNCmax + g * 32, raw);
             tmem_ld_wait();
@@ -712,6 +715,7 @@ void launch_slab_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 
 }  // namespace
 
+void set_gemm_dbg(int v) { g_gemm_dbg = v; }
 int smem_bytes_fwd(int) { return smem_total<kFwd>(); }
 int smem_bytes_dz(int) { return smem_total<kDz>(); }
 int smem_bytes_dh() { return smem_total<kDh>(); }
@@ -730,6 +734,7 @@ void launch_transpose_w(const __nv_bfloat16* W, __nv_bfloat16* Wt, int V, int H,
 void launch_joint_fwd(const Lattice& L, const JointDims& d, const CUtensorMap& tm_h, const CUtensorMap& tm_w,
                       const FwdArgs& a, int tile0, int n_tiles, int nc, cudaStream_t s) {
   GemmArgs g{};
+  g.dbg = g_gemm_dbg;
   g.L = L; g.tile0 = tile0; g.n_tiles_total = L.n_tiles_total; g.n_total = d.V; g.nc = nc; g.n_chunks = (d.V + nc - 1) / nc;
   g.k_blocks = (d.H + kBK - 1) / kBK; g.blank = d.blank; g.Umax = d.Umax; g.Vp = d.Vp; g.H = d.H;
   g.bias = a.bias; g.y = a.y; g.lse_tile = a.lse_tile; g.lpb = a.lpb; g.lpl = a.lpl;

@@ -82,6 +82,7 @@ void launch_joint_dw(const JointDims& d, const CUtensorMap& tm_dz_mn, const CUte
 void launch_greedy_argmax(const __nv_bfloat16* f, const __nv_bfloat16* g, const __nv_bfloat16* W, const float* bias,
                           const int* t_idx, int* out_k, int B, int Tmax, int V, int H, cudaStream_t s);
 
+void set_gemm_dbg(int v);
 int smem_bytes_fwd(int nc_total);
 int smem_bytes_dz(int nc_total);
 int smem_bytes_dh();
