@@ -387,7 +387,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           named_bar_sync(1, kEpiThreads);
           const int col = j * p.nc + sub * 64 + rc;
-          if (col < p.H && sub * 64 + rc < p.nc) {
+          if (!ghost && col < p.H && sub * 64 + rc < p.nc) {  // a ghost CTA's rows are uninitialised slab memory
             if (!do_dg) {
 #pragma unroll 4
               for (int a = 0; a < kTT; ++a) {
