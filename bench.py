@@ -162,6 +162,7 @@ def main():
     import ctypes
     import myrtlespeech_b200 as M
     from myrtlespeech_b200 import _lib
+    from myrtlespeech_b200 import parallel as par
     from myrtlespeech_b200.loss import RNNTLoss
     from myrtlespeech_b200.model import RNNTJoint
 
@@ -181,7 +182,7 @@ def main():
     Wd = W.to(dev).requires_grad_(True)
     bd = bias.to(dev).requires_grad_(True)
     fd.requires_grad_(True); gd.requires_grad_(True)
-    flat = torch.zeros(V * H + V + 2, dtype=torch.float32, device=dev)  # [dW | db | loss_sum | n]
+    flat = torch.zeros(par.flat_size(V, H), dtype=torch.float32, device=dev)  # [dW | db | loss_sum | n]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     def hot_step():
@@ -189,9 +190,8 @@ def main():
         total = loss.sum()
         total.backward()
         if world > 1:
-            flat[: V * H].copy_(Wd.grad.reshape(-1)); flat[V * H: V * H + V].copy_(bd.grad)
-            flat[V * H + V] = total.detach(); flat[V * H + V + 1] = float(B)
-            dist.all_reduce(flat)
+            par.pack_step(flat, Wd.grad, bd.grad, total.detach(), B)
+            par.allreduce_step(flat)
         fd.grad = gd.grad = Wd.grad = bd.grad = None
         return total
 
@@ -237,9 +237,8 @@ def main():
         loss = loss_mod(out, (y_dev, yl))
         loss.backward()
         if world > 1:
-            flat[: V * H].copy_(joint.fc.weight.grad.reshape(-1)); flat[V * H: V * H + V].copy_(joint.fc.bias.grad)
-            flat[V * H + V] = loss.detach(); flat[V * H + V + 1] = float(B)
-            dist.all_reduce(flat)
+            par.pack_step(flat, joint.fc.weight.grad, joint.fc.bias.grad, loss.detach(), B)
+            par.allreduce_step(flat)
         joint.zero_grad(set_to_none=True)
         return float(loss.item())  # device -> host read of the step's result
 
