@@ -34,7 +34,7 @@ constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
 constexpr int kMaxBiasCols = 2048;          // V (rounded up to chunks) supported by the smem bias table
-constexpr int kDhPitch = 65;                // fp32 pitch of the dpre transpose tile
+constexpr int kDhPitch = 68;                // fp32 pitch of the dpre tile (16-byte aligned rows, conflict-free 128-bit access)
 
 enum Epi { kFwd = 0, kDz = 1, kDh = 2 };
 int g_gemm_dbg = 0;
@@ -42,7 +42,7 @@ int g_gemm_dbg = 0;
 template <int EPI> struct Cfg;
 template <> struct Cfg<kFwd> { static constexpr int stages = 6; static constexpr int extra = kMaxBiasCols * 4; };
 template <> struct Cfg<kDz>  { static constexpr int stages = 4; static constexpr int extra = kMaxBiasCols * 4 + kBM * kNCmax * 2; };
-template <> struct Cfg<kDh>  { static constexpr int stages = 5; static constexpr int extra = kBM * kDhPitch * 4; };
+template <> struct Cfg<kDh>  { static constexpr int stages = 4; static constexpr int extra = 2 * kBM * kDhPitch * 4; };
 
 template <int EPI> constexpr int smem_total() { return Cfg<EPI>::stages * kStageBytes + Cfg<EPI>::extra + 1024 + 256; }
 
@@ -340,44 +340,70 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     } else {
       // ---- kDh ----
-      float* tile = reinterpret_cast<float*>(extra);
+      // Per 64-column sub-chunk: dpre = dh * (1 - h^2) is written to a double-buffered fp32 smem tile
+      // (row = lattice cell), then reduced over the 8 label positions (-> df) and the 16 frames (-> dg) of
+      // the tile with 128-bit smem reads and red.global.add.v4.  h for the NEXT sub-chunk is fetched before
+      // the current one is processed, so its L2 latency hides behind the arithmetic.
+      float* tile_base = reinterpret_cast<float*>(extra);
       const __nv_bfloat16* hrow = p.hslab + (static_cast<size_t>(m) * kBM + r) * p.H;
-      const int rc = et & 63;
-      const bool do_dg = et >= 64;
+      const int n_sub = (p.nc + 63) / 64;
+      const int total_sub = p.n_chunks * n_sub;
+      auto load_h = [&](int s_idx, uint4 (&hv)[8]) {
+        const int jj = s_idx / n_sub, ss = s_idx - jj * n_sub;
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          const int g = ss * 2 + gg;
+          const int c0 = jj * p.nc + g * 32;
+          const uint4* hp = reinterpret_cast<const uint4*>(hrow + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            hv[gg * 4 + q] = (g * 32 < p.nc && c0 + 8 * q < p.H) ? __ldg(hp + q) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      uint4 hcur[8];
+      load_h(0, hcur);
+      int s_idx = 0;
       for (int j = 0; j < p.n_chunks; ++j) {
         const int buf = j & 1;
         mbar_wait(&tfull_bar[buf], (j >> 1) & 1);
         tc_fence_after();
-        const int n_sub = (p.nc + 63) / 64;
-        for (int sub = 0; sub < n_sub; ++sub) {
+        for (int sub = 0; sub < n_sub; ++sub, ++s_idx) {
+          uint4 hnext[8];
+          if (s_idx + 1 < total_sub) {
+            load_h(s_idx + 1, hnext);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) hnext[q] = make_uint4(0, 0, 0, 0);
+          }
+          float* tile = tile_base + (s_idx & 1) * (kBM * kDhPitch);
 #pragma unroll
           for (int gg = 0; gg < 2; ++gg) {
             const int g = sub * 2 + gg;
             const int c0 = j * p.nc + g * 32;
-            float* trow = tile + r * kDhPitch + gg * 32;
+            float4* trow = reinterpret_cast<float4*>(tile + r * kDhPitch + gg * 32);
             if (g * 32 < p.nc && c0 < p.H) {
               uint32_t raw[32];
               tmem_ld32(lane_taddr + buf * kNCmax + g * 32, raw);
-              const uint4* hp = reinterpret_cast<const uint4*>(hrow + c0);
-              uint4 hv[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) hv[q] = (c0 + 8 * q < p.H) ? __ldg(hp + q) : make_uint4(0, 0, 0, 0);
               tmem_ld_wait();
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint32_t w[4] = {hv[q].x, hv[q].y, hv[q].z, hv[q].w};
+                const uint4 hq = hcur[gg * 4 + q];
+                const uint32_t w[4] = {hq.x, hq.y, hq.z, hq.w};
+                float o[8];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float h0 = bf16lo(w[e]), h1 = bf16hi(w[e]);
                   const float d0 = __uint_as_float(raw[8 * q + 2 * e]);
                   const float d1 = __uint_as_float(raw[8 * q + 2 * e + 1]);
-                  trow[8 * q + 2 * e] = fmaf(-h0 * h0, d0, d0);
-                  trow[8 * q + 2 * e + 1] = fmaf(-h1 * h1, d1, d1);
+                  o[2 * e] = fmaf(-h0 * h0, d0, d0);
+                  o[2 * e + 1] = fmaf(-h1 * h1, d1, d1);
                 }
+                trow[2 * q] = make_float4(o[0], o[1], o[2], o[3]);
+                trow[2 * q + 1] = make_float4(o[4], o[5], o[6], o[7]);
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) trow[i] = 0.0f;
+              for (int i = 0; i < 8; ++i) trow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
           if (sub == n_sub - 1) {
@@ -385,30 +411,39 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive_even_cta(&tempty_bar[buf]);
           }
-          named_bar_sync(1, kEpiThreads);
-          const int col = j * p.nc + sub * 64 + rc;
-          if (!ghost && col < p.H && sub * 64 + rc < p.nc) {  // a ghost CTA's rows are uninitialised slab memory
-            if (!do_dg) {
-#pragma unroll 4
-              for (int a = 0; a < kTT; ++a) {
-                float s = 0.0f;
+          named_bar_sync(1, kEpiThreads);  // tile[s_idx & 1] complete; also fences the buffer written two subs ago
+          const int c4 = et & 15;
+          const int colbase = j * p.nc + sub * 64 + 4 * c4;
+          if (!ghost && sub * 64 + 4 * c4 < p.nc && colbase < p.H) {  // a ghost CTA's rows are uninitialised memory
+            const float* tcol = tile + 4 * c4;
 #pragma unroll
-                for (int c = 0; c < kTU; ++c) s += tile[(a * kTU + c) * kDhPitch + rc];
-                if (ti.t0 + a < ti.T)
-                  red_add_f32(p.df + (static_cast<size_t>(ti.b) * p.L.Tmax + ti.t0 + a) * p.H + col, s);
-              }
-            } else {
-#pragma unroll 2
+            for (int k = 0; k < 2; ++k) {  // df: sum over the 8 label positions of frame a
+              const int a = (et >> 4) + 8 * k;
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
               for (int c = 0; c < kTU; ++c) {
-                float s = 0.0f;
-#pragma unroll
-                for (int a = 0; a < kTT; ++a) s += tile[(a * kTU + c) * kDhPitch + rc];
-                if (ti.u0 + c <= ti.U)
-                  red_add_f32(p.dg + (static_cast<size_t>(ti.b) * p.L.U1max + ti.u0 + c) * p.H + col, s);
+                const float4 v = *reinterpret_cast<const float4*>(tcol + (a * kTU + c) * kDhPitch);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
               }
+              if (ti.t0 + a < ti.T)
+                red_add_v4_f32(p.df + (static_cast<size_t>(ti.b) * p.L.Tmax + ti.t0 + a) * p.H + colbase, acc.x, acc.y,
+                               acc.z, acc.w);
+            }
+            {  // dg: sum over the 16 frames of label position c
+              const int c = et >> 4;
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int a = 0; a < kTT; ++a) {
+                const float4 v = *reinterpret_cast<const float4*>(tcol + (a * kTU + c) * kDhPitch);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+              }
+              if (ti.u0 + c <= ti.U)
+                red_add_v4_f32(p.dg + (static_cast<size_t>(ti.b) * p.L.U1max + ti.u0 + c) * p.H + colbase, acc.x, acc.y,
+                               acc.z, acc.w);
             }
           }
-          named_bar_sync(1, kEpiThreads);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) hcur[q] = hnext[q];
         }
       }
     }
