@@ -94,6 +94,8 @@ long long rnnt_debug_get(const char* key);                /* "launches": kernels
  * synchronises, sums the durations per kernel class (hgen, joint_fwd, joint_dz, joint_dh, joint_dw,
  * lattice, coefs, misc) into ms[0..8) / count[0..8) and clears the record. */
 int rnnt_debug_kernel_times(double* ms, long long* count, int n);
+/* Bring-up: %globaltimer stamps (8 per CTA) of the last tcgen05 GEMM launch made with gemm_dbg & 4. */
+int rnnt_debug_read_prof(unsigned long long* out, int n);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ using namespace rnnt;
 
 thread_local char g_err[512] = "";
 int g_slab_tiles_override = 0;
+int g_path = 1;  // 1 = persistent kernels (persist.cu), 0 = per-slab kernels (joint.cu)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -85,7 +86,7 @@ int sm_count() {
 struct Plan {
   int B, Tmax, Umax, U1, V, H, Vp, D;
   int max_tiles, slab_tiles;
-  size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_wt, o_h, o_dz;
+  size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_wt, o_h, o_dz, o_hs;
   size_t total;
 };
 
@@ -115,6 +116,7 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
   p.o_wt = take(2 * static_cast<size_t>(H) * p.Vp);
   p.o_h = take(2 * static_cast<size_t>(p.slab_tiles) * kTileRows * H);
   p.o_dz = take(2 * static_cast<size_t>(p.slab_tiles) * kTileRows * p.Vp);
+  p.o_hs = take(2 * static_cast<size_t>(kMaxPersistCtas) * 2 * kTileRows * H);
   p.total = o;
   return p;
 }
@@ -217,6 +219,7 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "slab_tiles")) g_slab_tiles_override = value;
   if (!strcmp(key, "time_kernels")) g_time_kernels = value != 0;
   if (!strcmp(key, "gemm_dbg")) set_gemm_dbg(value);
+  if (!strcmp(key, "path")) g_path = value;
   if (!strcmp(key, "reset_launches")) for (int i = 0; i < K_NCLASS; ++i) g_launches[i] = 0;
 }
 
@@ -229,6 +232,8 @@ long long rnnt_debug_get(const char* key) {
   if (!strcmp(key, "n_classes")) return K_NCLASS;
   return -1;
 }
+
+int rnnt_debug_read_prof(unsigned long long* out, int n) { return read_gemm_prof(out, n); }
 
 int rnnt_debug_kernel_times(double* ms, long long* count, int n) {
   if (n < K_NCLASS) return fail(RNNT_ERR_INVALID_ARGUMENT, "need room for %d classes", (int)K_NCLASS);
@@ -281,8 +286,24 @@ int rnnt_fused_forward(const void* f, const void* g, const void* W, const float*
   rc = make_map(&tm_w, W, H, V, H, 64, nc / 2);
   if (rc) return rc;
 
+  if (g_path == 1) {
+    int n_ctas = sm_count() < kMaxPersistCtas ? sm_count() : kMaxPersistCtas;
+    n_ctas &= ~1;
+    const int n_ptiles = (n_tiles + 1) / 2;
+    if (n_ctas > 2 * n_ptiles) n_ctas = 2 * n_ptiles;
+    CUtensorMap tm_hs;
+    rc = make_map(&tm_hs, w.at<void>(p.o_hs), H, static_cast<uint64_t>(kMaxPersistCtas) * 2 * kTileRows, H, 64, 128);
+    if (rc) return rc;
+    FwdPArgs pa{};
+    pa.L = L; pa.n_tiles_total = n_tiles; pa.V = V; pa.H = H; pa.nc = nc; pa.n_chunks = (V + nc - 1) / nc;
+    pa.k_blocks = (H + 63) / 64; pa.blank = blank; pa.Umax = d.Umax;
+    pa.f = static_cast<const __nv_bfloat16*>(f); pa.g = static_cast<const __nv_bfloat16*>(g);
+    pa.hscratch = w.at<__nv_bfloat16>(p.o_hs);
+    pa.bias = bias; pa.y = y; pa.lse_tile = w.at<float>(p.o_lse); pa.lpb = w.at<float>(p.o_lpb); pa.lpl = w.at<float>(p.o_lpl);
+    KLAUNCH(K_FWD, s, launch_fwd_persist(tm_hs, tm_w, pa, n_ctas, s));
+  }
   FwdArgs a{bias, y, w.at<float>(p.o_lse), w.at<float>(p.o_lpb), w.at<float>(p.o_lpl)};
-  for (int t0 = 0; t0 < n_tiles; t0 += p.slab_tiles) {
+  for (int t0 = 0; g_path != 1 && t0 < n_tiles; t0 += p.slab_tiles) {
     const int nt = (n_tiles - t0 < p.slab_tiles) ? n_tiles - t0 : p.slab_tiles;
     KLAUNCH(K_HGEN, s, launch_hgen(L, static_cast<const __nv_bfloat16*>(f), static_cast<const __nv_bfloat16*>(g),
                                    w.at<__nv_bfloat16>(p.o_h), t0, nt, H, s));

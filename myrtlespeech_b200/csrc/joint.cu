@@ -39,6 +39,15 @@ constexpr int kDhPitch = 68;                // fp32 pitch of the dpre tile (16-b
 enum Epi { kFwd = 0, kDz = 1, kDh = 2 };
 int g_gemm_dbg = 0;
 
+// bring-up profiling (gemm_dbg & 4): %globaltimer stamps of the last slab_gemm launch, 8 per CTA
+__device__ unsigned long long g_prof[160 * 8];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PROF(slot) do { if (p.dbg & 4) g_prof[blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
+
 template <int EPI> struct Cfg;
 template <> struct Cfg<kFwd> { static constexpr int stages = 6; static constexpr int extra = kMaxBiasCols * 4; };
 template <> struct Cfg<kDz>  { static constexpr int stages = 4; static constexpr int extra = kMaxBiasCols * 4 + kBM * kNCmax * 2; };
@@ -109,6 +118,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const bool ghost = (p.tile0 + m) >= p.n_tiles_total;
 
   if (threadIdx.x == 0) {
+    PROF(0);
     prefetch_tmap(&tm_a);
     prefetch_tmap(&tm_b);
     if (EPI == kDz) prefetch_tmap(&tm_out);
@@ -127,6 +137,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const TileInfo ti = *s_ti;
+  if (threadIdx.x == 0) PROF(1);
 
   const int nc_half = p.nc >> 1;
   const uint32_t b_bytes = static_cast<uint32_t>(nc_half) * kBK * 2;
@@ -164,6 +175,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (lane == 0) {
+          if (it == 0) PROF(2);
           const uint32_t a_addr = smem_u32(stage_base + s * kStageBytes);
           const uint32_t b_addr = a_addr + kAStage;
 #pragma unroll
@@ -178,6 +190,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         __syncwarp();
       }
     }
+    if (lane == 0) PROF(3);
   } else {
     // ------------------------------- epilogue ------------------------------------
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
@@ -208,6 +221,8 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const int buf = j & 1;
           mbar_wait(&tfull_bar[buf], (j >> 1) & 1);
           tc_fence_after();
+          if (et == 0 && j == 0) PROF(4);
+          if (et == 0 && j == p.n_chunks - 1) PROF(5);
           for (int g = 0; g < ((p.dbg & 1) ? 0 : p.nc / 32); ++g) {
             uint32_t raw[32];
             tmem_ld32(lane_taddr + buf * kNCmax + g * 32, raw);
@@ -244,6 +259,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           p.lpb[didx] = (zb - lse2) * kLn2;
           p.lpl[didx] = (u < ti.U) ? (zl - lse2) * kLn2 : kNeg;
         }
+        if (et == 0) PROF(6);
       } else {
         // ---- kDz ----
         uint8_t* stage_out = extra + kMaxBiasCols * 4;
@@ -455,6 +471,7 @@ slab_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, kTmemCols);
+    if (lane == 0) PROF(7);
   }
 }
 
@@ -751,6 +768,10 @@ void launch_slab_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 }  // namespace
 
 void set_gemm_dbg(int v) { g_gemm_dbg = v; }
+int read_gemm_prof(unsigned long long* out, int n) {
+  if (n > 160 * 8) n = 160 * 8;
+  return cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * n) == cudaSuccess ? n : -1;
+}
 int smem_bytes_fwd(int) { return smem_total<kFwd>(); }
 int smem_bytes_dz(int) { return smem_total<kDz>(); }
 int smem_bytes_dh() { return smem_total<kDh>(); }

@@ -82,7 +82,31 @@ void launch_joint_dw(const JointDims& d, const CUtensorMap& tm_dz_mn, const CUte
 void launch_greedy_argmax(const __nv_bfloat16* f, const __nv_bfloat16* g, const __nv_bfloat16* W, const float* bias,
                           const int* t_idx, int* out_k, int B, int Tmax, int V, int H, cudaStream_t s);
 
+// ---- persist.cu -------------------------------------------------------------------------------
+constexpr int kMaxPersistCtas = 148;  // scratch is sized for this many CTAs (one per B200 SM)
+
+struct FwdPArgs {
+  Lattice L;
+  int n_tiles_total;
+  int V, H;
+  int nc, n_chunks, k_blocks;
+  int blank, Umax;
+  const __nv_bfloat16* f;     // [B][Tmax][H]
+  const __nv_bfloat16* g;     // [B][U1max][H]
+  __nv_bfloat16* hscratch;    // [n_ctas][2][128][H]  per-CTA double-buffered h tiles (L2-resident)
+  const float* bias;
+  const int* y;
+  float* lse_tile;
+  float* lpb;
+  float* lpl;
+};
+// One persistent launch for the whole batch: hgen + logits (tcgen05) + online log-softmax.
+void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
+                        cudaStream_t s);
+int smem_bytes_fwd_persist();
+
 void set_gemm_dbg(int v);
+int read_gemm_prof(unsigned long long* out, int n);
 int smem_bytes_fwd(int nc_total);
 int smem_bytes_dz(int nc_total);
 int smem_bytes_dh();
