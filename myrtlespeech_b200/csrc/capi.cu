@@ -24,6 +24,7 @@ using namespace rnnt;
 thread_local char g_err[512] = "";
 int g_slab_tiles_override = 0;
 int g_path = 1;  // 1 = persistent kernels (persist.cu), 0 = per-slab kernels (joint.cu)
+int g_ring_slots = 2;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -86,7 +87,8 @@ int sm_count() {
 struct Plan {
   int B, Tmax, Umax, U1, V, H, Vp, D;
   int max_tiles, slab_tiles;
-  size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_wt, o_h, o_dz, o_hs;
+  size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_wt, o_h, o_dz, o_hs, o_hring, o_dzring, o_flags;
+  int mega_ok, n_vt, n_ht, n_out, KG, C, P, NS;
   size_t total;
 };
 
@@ -117,6 +119,20 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
   p.o_h = take(2 * static_cast<size_t>(p.slab_tiles) * kTileRows * H);
   p.o_dz = take(2 * static_cast<size_t>(p.slab_tiles) * kTileRows * p.Vp);
   p.o_hs = take(2 * static_cast<size_t>(kMaxPersistCtas) * 2 * kTileRows * H);
+  // backward mega-kernel: role split of the 74 CTA pairs (see persist.cu)
+  p.n_vt = (p.Vp + 255) / 256; p.n_ht = (H + 511) / 512; p.n_out = p.n_vt * p.n_ht;
+  p.KG = (2 * (kMaxPersistCtas / 2) / 3 + p.n_out) / (2 * p.n_out);  // round((n_pairs / 3) / n_out)
+  if (p.KG < 1) p.KG = 1;
+  p.C = p.n_out * p.KG;
+  p.P = kMaxPersistCtas / 2 - p.C;
+  p.NS = g_ring_slots;
+  p.mega_ok = p.C <= 40 && p.P >= 1;
+  p.o_hring = p.o_dzring = p.o_flags = 0;
+  if (p.mega_ok) {
+    p.o_hring = take(2 * static_cast<size_t>(p.P) * kMaxRingSlots * 2 * kTileRows * H);
+    p.o_dzring = take(2 * static_cast<size_t>(p.P) * kMaxRingSlots * 2 * kTileRows * p.Vp);
+    p.o_flags = take(sizeof(unsigned) * 2 * (kMaxPersistCtas / 2) * kMaxRingSlots);
+  }
   p.total = o;
   return p;
 }
@@ -220,6 +236,7 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "time_kernels")) g_time_kernels = value != 0;
   if (!strcmp(key, "gemm_dbg")) set_gemm_dbg(value);
   if (!strcmp(key, "path")) g_path = value;
+  if (!strcmp(key, "ring_slots") && value >= 2 && value <= 4) g_ring_slots = value;
   if (!strcmp(key, "reset_launches")) for (int i = 0; i < K_NCLASS; ++i) g_launches[i] = 0;
 }
 
@@ -233,7 +250,7 @@ long long rnnt_debug_get(const char* key) {
   return -1;
 }
 
-int rnnt_debug_read_prof(unsigned long long* out, int n) { return read_gemm_prof(out, n); }
+int rnnt_debug_read_prof(unsigned long long* out, int n) { return g_path == 1 ? read_persist_prof(out, n) : read_gemm_prof(out, n); }
 
 int rnnt_debug_kernel_times(double* ms, long long* count, int n) {
   if (n < K_NCLASS) return fail(RNNT_ERR_INVALID_ARGUMENT, "need room for %d classes", (int)K_NCLASS);
@@ -295,7 +312,7 @@ int rnnt_fused_forward(const void* f, const void* g, const void* W, const float*
     rc = make_map(&tm_hs, w.at<void>(p.o_hs), H, static_cast<uint64_t>(kMaxPersistCtas) * 2 * kTileRows, H, 64, 128);
     if (rc) return rc;
     FwdPArgs pa{};
-    pa.L = L; pa.n_tiles_total = n_tiles; pa.V = V; pa.H = H; pa.nc = nc; pa.n_chunks = (V + nc - 1) / nc;
+    pa.L = L; pa.dbg = get_gemm_dbg(); pa.n_tiles_total = n_tiles; pa.V = V; pa.H = H; pa.nc = nc; pa.n_chunks = (V + nc - 1) / nc;
     pa.k_blocks = (H + 63) / 64; pa.blank = blank; pa.Umax = d.Umax;
     pa.f = static_cast<const __nv_bfloat16*>(f); pa.g = static_cast<const __nv_bfloat16*>(g);
     pa.hscratch = w.at<__nv_bfloat16>(p.o_hs);
@@ -345,6 +362,33 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
   KLAUNCH(K_MISC, s, launch_transpose_w(static_cast<const __nv_bfloat16*>(W), w.at<__nv_bfloat16>(p.o_wt), V, H, p.Vp, s));
 
   const int nc_v = chunk_cols(V), nc_h = chunk_cols(H);
+  if (g_path == 1 && p.mega_ok && sm_count() >= kMaxPersistCtas) {
+    const uint64_t ring_rows = static_cast<uint64_t>(p.P) * p.NS * 2 * kTileRows;
+    CUtensorMap tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn;
+    if ((rc = make_map(&tm_h, w.at<void>(p.o_hring), H, ring_rows, H, 64, 128))) return rc;
+    if ((rc = make_map(&tm_w, W, H, V, H, 64, nc_v / 2))) return rc;
+    if ((rc = make_map(&tm_dz, w.at<void>(p.o_dzring), p.Vp, ring_rows, p.Vp, 64, 128))) return rc;
+    if ((rc = make_map(&tm_wt, w.at<void>(p.o_wt), p.Vp, H, p.Vp, 64, nc_h / 2))) return rc;
+    if ((rc = make_map(&tm_dz_mn, w.at<void>(p.o_dzring), p.Vp, ring_rows, p.Vp, 64, 64))) return rc;
+    if ((rc = make_map(&tm_h_mn, w.at<void>(p.o_hring), H, ring_rows, H, 64, 64))) return rc;
+    const size_t n_flags = static_cast<size_t>(kMaxPersistCtas / 2) * kMaxRingSlots;
+    CUDA_TRY(cudaMemsetAsync(w.at<unsigned>(p.o_flags), 0, sizeof(unsigned) * 2 * n_flags, s));
+    BwdPArgs a{};
+    a.L = L; a.dbg = get_gemm_dbg(); a.n_tiles_total = n_tiles; a.V = V; a.H = H; a.Vp = p.Vp;
+    a.nc_v = nc_v; a.n_chunks_v = (V + nc_v - 1) / nc_v; a.kb_h = (H + 63) / 64;
+    a.nc_h = nc_h; a.n_chunks_h = (H + nc_h - 1) / nc_h; a.kb_v = p.Vp / 64;
+    a.blank = blank; a.Umax = d.Umax;
+    a.P = p.P; a.C = p.C; a.KG = p.KG; a.NS = p.NS; a.n_vt = p.n_vt; a.n_ht = p.n_ht; a.n_out = p.n_out;
+    a.f = static_cast<const __nv_bfloat16*>(f); a.g = static_cast<const __nv_bfloat16*>(g);
+    a.h_ring = w.at<__nv_bfloat16>(p.o_hring);
+    a.bias = bias; a.y = y; a.lse_tile = w.at<float>(p.o_lse); a.lpb = w.at<float>(p.o_lpb); a.lpl = w.at<float>(p.o_lpl);
+    a.c1 = w.at<float>(p.o_c1); a.c2 = w.at<float>(p.o_c2); a.grad_loss = grad_loss;
+    a.db = db; a.df = df; a.dg = dg; a.dW = dW;
+    a.ready = w.at<unsigned>(p.o_flags); a.done = w.at<unsigned>(p.o_flags) + n_flags;
+    KLAUNCH(K_DZ, s, launch_bwd_mega(tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, a, 2 * (p.P + p.C), s));
+    CUDA_TRY(cudaGetLastError());
+    return RNNT_OK;
+  }
   const uint64_t slab_rows = static_cast<uint64_t>(p.slab_tiles) * kTileRows;
   CUtensorMap tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn;
   if ((rc = make_map(&tm_h, w.at<void>(p.o_h), H, slab_rows, H, 64, 128))) return rc;

@@ -768,6 +768,7 @@ void launch_slab_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 }  // namespace
 
 void set_gemm_dbg(int v) { g_gemm_dbg = v; }
+int get_gemm_dbg() { return g_gemm_dbg; }
 int read_gemm_prof(unsigned long long* out, int n) {
   if (n > 160 * 8) n = 160 * 8;
   return cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * n) == cudaSuccess ? n : -1;

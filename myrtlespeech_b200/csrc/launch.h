@@ -84,9 +84,11 @@ void launch_greedy_argmax(const __nv_bfloat16* f, const __nv_bfloat16* g, const 
 
 // ---- persist.cu -------------------------------------------------------------------------------
 constexpr int kMaxPersistCtas = 148;  // scratch is sized for this many CTAs (one per B200 SM)
+constexpr int kMaxRingSlots = 4;
 
 struct FwdPArgs {
   Lattice L;
+  int dbg;
   int n_tiles_total;
   int V, H;
   int nc, n_chunks, k_blocks;
@@ -104,6 +106,42 @@ struct FwdPArgs {
 void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
                         cudaStream_t s);
 int smem_bytes_fwd_persist();
+int read_persist_prof(unsigned long long* out, int n);
+int get_gemm_dbg();
+
+struct BwdPArgs {
+  Lattice L;
+  int dbg;
+  int n_tiles_total;
+  int V, H, Vp;
+  int nc_v, n_chunks_v, kb_h;  // dz pass: N chunks over V, k-blocks over H
+  int nc_h, n_chunks_h, kb_v;  // dh pass: N chunks over H, k-blocks over Vp
+  int blank, Umax;
+  int P, C, KG, NS;            // producer pairs, consumer pairs, K-groups, ring slots per producer pair
+  int n_vt, n_ht, n_out;       // dW blocks of 256 (V) x 512 (H); n_out = n_vt * n_ht consumers per K-group
+  const __nv_bfloat16* f;
+  const __nv_bfloat16* g;
+  __nv_bfloat16* h_ring;       // [P][NS][256][H]
+  const float* bias;
+  const int* y;
+  const float* lse_tile;
+  const float* lpb;
+  const float* lpl;
+  const float* c1;
+  const float* c2;
+  const float* grad_loss;
+  float* db;
+  float* df;
+  float* dg;
+  float* dW;
+  unsigned* ready;             // [P][NS] += 1 per producer CTA per use
+  unsigned* done;              // [P][NS] += 1 per consumer pair per use
+};
+// One persistent launch for the whole backward pass (see persist.cu).
+void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUtensorMap& tm_dz, const CUtensorMap& tm_wt,
+                     const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, const BwdPArgs& a, int n_ctas,
+                     cudaStream_t s);
+int smem_bytes_bwd_mega();
 
 void set_gemm_dbg(int v);
 int read_gemm_prof(unsigned long long* out, int n);
