@@ -364,7 +364,8 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
   const int nc_v = chunk_cols(V), nc_h = chunk_cols(H);
   if (g_path == 1 && p.mega_ok && sm_count() >= kMaxPersistCtas) {
     const uint64_t ring_rows = static_cast<uint64_t>(p.P) * p.NS * 2 * kTileRows;
-    CUtensorMap tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn;
+    CUtensorMap tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st;
+    if ((rc = make_map(&tm_dz_st, w.at<void>(p.o_dzring), p.Vp, ring_rows, p.Vp, 64, 32))) return rc;
     if ((rc = make_map(&tm_h, w.at<void>(p.o_hring), H, ring_rows, H, 64, 128))) return rc;
     if ((rc = make_map(&tm_w, W, H, V, H, 64, nc_v / 2))) return rc;
     if ((rc = make_map(&tm_dz, w.at<void>(p.o_dzring), p.Vp, ring_rows, p.Vp, 64, 128))) return rc;
@@ -385,7 +386,7 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
     a.c1 = w.at<float>(p.o_c1); a.c2 = w.at<float>(p.o_c2); a.grad_loss = grad_loss;
     a.db = db; a.df = df; a.dg = dg; a.dW = dW;
     a.ready = w.at<unsigned>(p.o_flags); a.done = w.at<unsigned>(p.o_flags) + n_flags;
-    KLAUNCH(K_DZ, s, launch_bwd_mega(tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, a, 2 * (p.P + p.C), s));
+    KLAUNCH(K_DZ, s, launch_bwd_mega(tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a, 2 * (p.P + p.C), s));
     CUDA_TRY(cudaGetLastError());
     return RNNT_OK;
   }

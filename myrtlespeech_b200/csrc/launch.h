@@ -134,13 +134,13 @@ struct BwdPArgs {
   float* df;
   float* dg;
   float* dW;
-  unsigned* ready;             // [P][NS] += 1 per producer CTA per use
+  unsigned* ready;             // [P][NS] += 1 per producer epilogue warp (2 CTAs x 8) per use
   unsigned* done;              // [P][NS] += 1 per consumer pair per use
 };
 // One persistent launch for the whole backward pass (see persist.cu).
 void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUtensorMap& tm_dz, const CUtensorMap& tm_wt,
-                     const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, const BwdPArgs& a, int n_ctas,
-                     cudaStream_t s);
+                     const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, const CUtensorMap& tm_dz_st,
+                     const BwdPArgs& a, int n_ctas, cudaStream_t s);
 int smem_bytes_bwd_mega();
 
 void set_gemm_dbg(int v);

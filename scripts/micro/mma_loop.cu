@@ -1,0 +1,172 @@
+// Microbenchmark 3: the real kernels' MMA issue loop (full/empty mbarrier ring, producer thread without TMA,
+// tcgen05.fence, 4 MMAs per k-block, multicast commit) with each ingredient switchable, to find what
+// stretches a k-block from the 512-cycle floor to ~760 cycles.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../myrtlespeech_b200/csrc/ptx.cuh"
+using namespace rnnt;
+
+struct Cfg {
+  int n_kb;        // k-blocks
+  int stages;
+  int use_full;    // MMA thread waits on full barriers fed by a producer thread
+  int fence;       // tcgen05.fence::after_thread_sync after each full wait
+  int mask;        // commit multicast mask (1 or 3)
+  int all_lanes;   // all 32 lanes spin on the barrier (as in the kernels) vs only lane 0
+  int chunk_kb;    // switch accumulator buffer + extra commit every chunk_kb k-blocks (0 = never)
+  int epi;         // epilogue warps: 0 none, 1 tcgen05.ld the other buffer continuously
+  int lean;        // 1: whole loop inside lane 0, incremental stage/phase, no per-iteration reconvergence; 2: + poll-ahead
+};
+
+__global__ void __launch_bounds__(192, 1) mma_loop_kernel(Cfg c, long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[8], empty_bar[8], done_bar, tfull_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ volatile int stop_flag;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = threadIdx.x; i < 192 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&done_bar, 1); mbar_init(&tfull_bar, 1);
+    stop_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc_2cta(&tmem_slot, 512); tmem_relinquish_2cta(); }
+  fence_proxy_async_smem();
+  tc_fence_before(); __syncthreads(); cluster_sync_all(); tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    if (lane == 0 && c.use_full && rank == 0) {
+      for (int it = 0; it < c.n_kb; ++it) {
+        const int s = it % c.stages;
+        mbar_wait(&empty_bar[s], ((it / c.stages) & 1) ^ 1);
+        mbar_arrive(&full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, 256, false, false);
+      const uint32_t base = smem_u32(smem);
+      const long long t0 = clock64();
+      if (c.lean == 3) {
+        // converged warp, uniform control flow; only the MMA / commit instructions are predicated on elect.sync
+        int s = 0; uint32_t ph = 0; int in_chunk = 0; int buf = 0;
+        const int stages = c.stages, chunk_kb = c.chunk_kb;
+        const int use_full = c.use_full;
+        bool ready = use_full ? mbar_try_wait(&full_bar[0], 0) : true;
+        for (int it = 0; it < c.n_kb; ++it) {
+          if (!ready) mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = base + s * 32768;
+          const uint64_t ad = make_smem_desc_sw128(a_addr, 16, 1024), bd = make_smem_desc_sw128(a_addr + 16384, 16, 1024);
+          const uint32_t d = tmem + buf * 256;
+          const bool last = (++in_chunk == chunk_kb);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16_pair(d, ad + 2 * kk, bd + 2 * kk, idesc, 1u);
+            umma_commit_pair(&empty_bar[s], 3);
+            if (last) umma_commit_pair(&tfull_bar, 3);
+          }
+          __syncwarp();
+          if (last) { in_chunk = 0; buf ^= 1; }
+          if (++s == stages) { s = 0; ph ^= 1; }
+          ready = use_full ? mbar_try_wait(&full_bar[s], ph) : true;
+        }
+      } else if (c.lean) {
+        if (lane == 0) {
+          int s = 0; uint32_t ph = 0; int in_chunk = 0; int buf = 0;
+          const int stages = c.stages, chunk_kb = c.chunk_kb, lean = c.lean;
+          bool ready = false;
+          const int use_full = c.use_full, fence = c.fence;
+          if (lean == 2 && use_full) ready = mbar_try_wait(&full_bar[0], 0);
+          for (int it = 0; it < c.n_kb; ++it) {
+            if (use_full && !ready) mbar_wait(&full_bar[s], ph);
+            if (fence) tc_fence_after();
+            const uint32_t a_addr = base + s * 32768;
+            const uint64_t ad = make_smem_desc_sw128(a_addr, 16, 1024), bd = make_smem_desc_sw128(a_addr + 16384, 16, 1024);
+            const uint32_t d = tmem + buf * 256;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16_pair(d, ad + 2 * kk, bd + 2 * kk, idesc, 1u);
+            umma_commit_pair(c.epi == 2 ? &empty_bar[0] : &empty_bar[s], c.mask);
+            if (++in_chunk == chunk_kb) { in_chunk = 0; umma_commit_pair(&tfull_bar, c.mask); buf ^= 1; }
+            if (++s == stages) { s = 0; ph ^= 1; }
+            ready = (lean == 2 && use_full) ? mbar_try_wait(&full_bar[s], ph) : false;
+          }
+        }
+        __syncwarp();
+      } else
+      for (int it = 0; it < c.n_kb; ++it) {
+        const int s = it % c.stages;
+        if (c.use_full) {
+          if (c.all_lanes || lane == 0) mbar_wait(&full_bar[s], (it / c.stages) & 1);
+          if (c.fence) tc_fence_after();
+        }
+        if (lane == 0) {
+          const int buf = c.chunk_kb ? ((it / c.chunk_kb) & 1) : 0;
+          const uint32_t a_addr = base + s * 32768;
+          const uint64_t ad = make_smem_desc_sw128(a_addr, 16, 1024), bd = make_smem_desc_sw128(a_addr + 16384, 16, 1024);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16_pair(tmem + buf * 256, ad + 2 * kk, bd + 2 * kk, idesc, 1u);
+          umma_commit_pair(&empty_bar[s], c.mask);
+          if (c.chunk_kb && (it % c.chunk_kb) == c.chunk_kb - 1) umma_commit_pair(&tfull_bar, c.mask);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit_pair(&done_bar, 1);
+      __syncwarp();
+      mbar_wait(&done_bar, 0);
+      const long long t1 = clock64();
+      if (lane == 0) { out_cycles[blockIdx.x] = t1 - t0; stop_flag = 1; }
+    }
+  } else if (c.epi) {
+    // epilogue-like TMEM readers on buffer 1 (values irrelevant)
+    const uint32_t lane_taddr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    float acc = 0.f;
+    while (!stop_flag && rank == 0) {
+      for (int g = 0; g < 8; ++g) {
+        uint32_t raw[32];
+        tmem_ld32(lane_taddr + 256 + g * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += __uint_as_float(raw[i]);
+      }
+    }
+    if (acc == 123.456f) out_cycles[147] = 1;
+  }
+  tc_fence_before(); __syncthreads(); cluster_sync_all();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_2cta(tmem, 512); }
+}
+
+int main(int argc, char** argv) {
+  long long* d_out; cudaMalloc(&d_out, sizeof(long long) * 148);
+  const int smem = 200 * 1024;
+  cudaFuncSetAttribute(mma_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  Cfg cfgs[] = {
+    {2048, 6, 0, 0, 3, 1, 16, 0, 3}, {2048, 6, 1, 1, 3, 1, 16, 0, 3}, {2048, 6, 1, 1, 3, 1, 16, 1, 3},
+    {2048, 6, 1, 1, 3, 1, 16, 0, 2},
+  };
+  for (auto& c : cfgs) {
+    for (int grid : {148}) {
+      cudaLaunchConfig_t lc{}; lc.gridDim = dim3(grid); lc.blockDim = dim3(192); lc.dynamicSmemBytes = smem; lc.stream = 0;
+      cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.attrs = at; lc.numAttrs = 1;
+      cudaMemset(d_out, 0, sizeof(long long) * 148);
+      for (int rep = 0; rep < 2; ++rep) {
+        cudaError_t le = cudaLaunchKernelEx(&lc, mma_loop_kernel, c, d_out);
+        if (le != cudaSuccess) printf("launch error %s\n", cudaGetErrorString(le));
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+      }
+      long long h[148]; cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+      long long mx = 0; for (int i = 0; i < grid; i += 2) if (h[i] > mx) mx = h[i];
+      printf("grid=%3d stages=%d full=%d fence=%d mask=%d all_lanes=%d chunk=%2d epi=%d lean=%d : %7.1f cyc/k-block (%5.1f per MMA)\n", grid,
+             c.stages, c.use_full, c.fence, c.mask, c.all_lanes, c.chunk_kb, c.epi, c.lean, (double)mx / c.n_kb, (double)mx / c.n_kb / 4);
+      fflush(stdout);
+    }
+  }
+  return 0;
+}
