@@ -33,7 +33,8 @@ WORKLOADS = {
     "c2": (32, 500, 100, 29, 512, "configs[1] chars: B=32 T=500 U=100 V=29 H=512 bf16"),
 }
 METRIC = "rnnt_joint_loss_fwd_bwd_utterances_per_s"
-KCLASSES = ["hgen", "joint_fwd", "joint_dz", "joint_dh", "joint_dw", "lattice", "coefs", "misc"]
+KCLASSES = ["hgen", "joint_fwd", "joint_dz", "joint_dh", "joint_dw", "lattice", "coefs", "misc", "joint_bwd_mega"]
+NK = 16
 
 
 def load_peaks():
@@ -44,6 +45,17 @@ def load_peaks():
         return dict(tflops_burst=p["bf16_tflops"], tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
                     hbm_gbs=p["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
     return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def ncu_traffic(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu summary
+    (profiles/traffic.json, written from an `ncu --set full` capture); None if that kernel was not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(workload, {}).get(kernel)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -154,7 +166,7 @@ def main():
         run_reference(args, B, T, U, V, H, desc, rank)
         return
 
-    args.steps = 20 if args.steps is None else args.steps
+    args.steps = 50 if args.steps is None else args.steps
     args.warmup = 5 if args.warmup is None else max(args.warmup, 3)
 
     import torch
@@ -255,8 +267,8 @@ def main():
     lib.rnnt_debug_set(b"time_kernels", 1)
     flush.zero_()
     hot_step()
-    kms = (ctypes.c_double * 8)(); kn = (ctypes.c_longlong * 8)()
-    _lib.check(lib.rnnt_debug_kernel_times(kms, kn, 8))
+    kms = (ctypes.c_double * NK)(); kn = (ctypes.c_longlong * NK)()
+    _lib.check(lib.rnnt_debug_kernel_times(kms, kn, NK))
     lib.rnnt_debug_set(b"time_kernels", 0)
 
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
@@ -266,23 +278,34 @@ def main():
 
     if rank == 0:
         n_rows = B * T * (U + 1)
-        flops = {"joint_fwd": 2.0 * n_rows * H * V, "joint_dz": 2.0 * n_rows * H * V, "joint_dh": 2.0 * n_rows * H * V,
-                 "joint_dw": 2.0 * n_rows * H * V}
+        # ALGORITHMIC flops per kernel class (forward 2NHV, backward 4NHV; the logits recompute of the
+        # backward pass is extra hardware work and is reported separately as hw_tflops)
+        nhv = float(n_rows) * H * V
+        flops = {"joint_fwd": 2.0 * nhv, "joint_dz": 0.0, "joint_dh": 2.0 * nhv, "joint_dw": 2.0 * nhv,
+                 "joint_bwd_mega": 4.0 * nhv}
+        hw_flops = {"joint_fwd": 2.0 * nhv, "joint_dz": 2.0 * nhv, "joint_dh": 2.0 * nhv, "joint_dw": 2.0 * nhv,
+                    "joint_bwd_mega": 6.0 * nhv}
         kernels = {}
         for i, name in enumerate(KCLASSES):
             if kn[i]:
                 kernels[name] = {"launches": int(kn[i]), "ms_per_step": round(kms[i], 4)}
                 if name in flops:
                     kernels[name]["tflops"] = round(flops[name] / (kms[i] * 1e-3) / 1e12, 1)
+                    kernels[name]["hw_tflops"] = round(hw_flops[name] / (kms[i] * 1e-3) / 1e12, 1)
         tensor_bound = V * H >= 1 << 18
         if tensor_bound:
             dom = max(flops, key=lambda k: kernels.get(k, {}).get("ms_per_step", 0.0))
             achieved = kernels[dom]["tflops"]
             roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops_sustained"],
                         "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4),
-                        "frac_of_burst": round(achieved / peaks["tflops_burst"], 4), "traffic": None,
+                        "frac_of_burst": round(achieved / peaks["tflops_burst"], 4),
+                        "hw_achieved": kernels[dom]["hw_tflops"],
+                        "hw_frac": round(kernels[dom]["hw_tflops"] / peaks["tflops_sustained"], 4),
+                        "traffic": ncu_traffic(dom, args.workload),
                         "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                        "algorithmic_flops_per_launch": flops[dom] / kernels[dom]["launches"]}
+                        "algorithmic_flops_per_launch": flops[dom] / kernels[dom]["launches"],
+                        "note": "achieved = algorithmic flops (logits recompute not counted) / CUDA-event duration of "
+                                "the launch; hw_achieved counts the recompute GEMM too"}
         else:
             # V=29: the path is bound by the tanh/exp special-function work and the lattice scalars, not tensor
             # cores; report HBM traffic of the per-cell lattice arrays (32 B/row) over lattice time

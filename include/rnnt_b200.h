@@ -88,11 +88,13 @@ int rnnt_greedy_joint_argmax(const void* f, const void* g, const void* W, const 
 /* Debug / test hooks (not part of the drop-in surface). */
 int rnnt_debug_copy_stats(const void* workspace, int B, int Tmax, int Umax, int V, int H, float* lp_blank,
                           float* lp_label, float* c_blank, float* c_label, float* lnp_beta, void* stream);
-void rnnt_debug_set(const char* key, int value);          /* "slab_tiles", "time_kernels", "reset_launches" */
+void rnnt_debug_set(const char* key, int value);          /* "slab_tiles", "time_kernels", "reset_launches",
+                                                              "path" (1 persistent kernels, 0 per-slab kernels),
+                                                              "ring_slots" (2..4), "gemm_dbg" (bring-up switches) */
 long long rnnt_debug_get(const char* key);                /* "launches": kernels launched since the last reset */
 /* In "time_kernels" mode every kernel launch is bracketed by CUDA events on its stream; this call
  * synchronises, sums the durations per kernel class (hgen, joint_fwd, joint_dz, joint_dh, joint_dw,
- * lattice, coefs, misc) into ms[0..8) / count[0..8) and clears the record. */
+ * lattice, coefs, misc, joint_bwd_mega) into ms[0..9) / count[0..9) and clears the record (n >= 9). */
 int rnnt_debug_kernel_times(double* ms, long long* count, int n);
 /* Bring-up: %globaltimer stamps (8 per CTA) of the last tcgen05 GEMM launch made with gemm_dbg & 4. */
 int rnnt_debug_read_prof(unsigned long long* out, int n);

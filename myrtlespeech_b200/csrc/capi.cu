@@ -43,7 +43,7 @@ int fail(int code, const char* fmt, ...) {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- launch accounting (rnnt_debug_get / rnnt_debug_kernel_times) ---------------------------------
-enum KClass { K_HGEN = 0, K_FWD, K_DZ, K_DH, K_DW, K_LATTICE, K_COEFS, K_MISC, K_NCLASS };
+enum KClass { K_HGEN = 0, K_FWD, K_DZ, K_DH, K_DW, K_LATTICE, K_COEFS, K_MISC, K_BWD_MEGA, K_NCLASS };
 long long g_launches[K_NCLASS] = {0};
 bool g_time_kernels = false;
 std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_pairs[K_NCLASS];
@@ -386,7 +386,7 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
     a.c1 = w.at<float>(p.o_c1); a.c2 = w.at<float>(p.o_c2); a.grad_loss = grad_loss;
     a.db = db; a.df = df; a.dg = dg; a.dW = dW;
     a.ready = w.at<unsigned>(p.o_flags); a.done = w.at<unsigned>(p.o_flags) + n_flags;
-    KLAUNCH(K_DZ, s, launch_bwd_mega(tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a, 2 * (p.P + p.C), s));
+    KLAUNCH(K_BWD_MEGA, s, launch_bwd_mega(tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a, 2 * (p.P + p.C), s));
     CUDA_TRY(cudaGetLastError());
     return RNNT_OK;
   }

@@ -181,7 +181,7 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     // The warp stays converged; only the issuing instructions run under elect.sync (lean SASS, see the note
     // at the MMA issuer).
     {
-      int s = 0, it = 0;
+      int s = 0, it = 0, n_issued = 0;
       uint32_t ph = 0;
       long long w_hfull = 0, w_empty = 0;
       const uint32_t sbase = smem_u32(stage_base);
@@ -193,7 +193,9 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             { PCNT_BEGIN(a); mbar_wait(&empty_bar[s], ph ^ 1); PCNT_END(a, w_empty); }
             // bring-up: dbg & 8 skips the A loads, dbg & 16 the B loads (L2-feed sensitivity; results are garbage)
             const uint32_t tx = ((p.dbg & 8) ? 0u : kAStage) + ((p.dbg & 16) ? 0u : b_bytes);
-            if (elect_one()) {
+            if ((p.dbg & 256) && n_issued >= kStages) {  // bring-up: no TMA traffic after the first ring fill
+              if (leader && elect_one()) mbar_arrive(&full_bar[s]);
+            } else if (elect_one()) {
               if (leader) { if (tx) mbar_arrive_expect_tx(&full_bar[s], 2 * tx); else mbar_arrive(&full_bar[s]); }
               const uint32_t sa = sbase + s * kStageBytes;
               if (!(p.dbg & 8)) tma_load_2d_pair_a(sa, &tm_a, &full_bar[s], k * kBK, a_row0 + hb * kBM);
@@ -201,6 +203,7 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 tma_load_2d_pair_a(sa + kAStage, &tm_b, &full_bar[s], k * kBK, j * p.nc + static_cast<int>(rank) * nc_half);
             }
             __syncwarp();
+            ++n_issued;
             if (++s == kStages) { s = 0; ph ^= 1; }
           }
         }
@@ -471,7 +474,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     if (warp == kMegaTmaWarp) {
       // ------------------------------- TMA producer (converged warp, elect.sync issue) ----------
       {
-        int s = 0, it = 0;
+        int s = 0, it = 0, n_issued = 0;
         uint32_t ph = 0;
         long long w_hfull = 0, w_empty = 0, w_dzr = 0;
         const uint32_t sbase = smem_u32(stage_base);
@@ -482,13 +485,16 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           for (int j = 0; j < p.n_chunks_v; ++j) {
             for (int k = 0; k < p.kb_h; ++k) {
               { PCNT_BEGIN(a); mbar_wait(&empty_bar[s], ph ^ 1); PCNT_END(a, w_empty); }
-              if (elect_one()) {
+              if ((p.dbg & 256) && n_issued >= kStages) {
+                if (leader && elect_one()) mbar_arrive(&full_bar[s]);
+              } else if (elect_one()) {
                 if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * (kAStage + bv_bytes));
                 const uint32_t sa = sbase + s * kStageBytes;
                 tma_load_2d_pair_a(sa, &tm_h, &full_bar[s], k * kBK, ring_row);
                 tma_load_2d_pair_a(sa + kAStage, &tm_w, &full_bar[s], k * kBK, j * p.nc_v + static_cast<int>(rank) * ncv_half);
               }
               __syncwarp();
+              ++n_issued;
               if (++s == kStages) { s = 0; ph ^= 1; }
             }
           }
@@ -504,13 +510,16 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 }
               }
               { PCNT_BEGIN(a); mbar_wait(&empty_bar[s], ph ^ 1); PCNT_END(a, w_empty); }
-              if (elect_one()) {
+              if ((p.dbg & 256) && n_issued >= kStages) {
+                if (leader && elect_one()) mbar_arrive(&full_bar[s]);
+              } else if (elect_one()) {
                 if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * (kAStage + bh_bytes));
                 const uint32_t sa = sbase + s * kStageBytes;
                 tma_load_2d_pair_a(sa, &tm_dz, &full_bar[s], k * kBK, ring_row);
                 tma_load_2d_pair_a(sa + kAStage, &tm_wt, &full_bar[s], k * kBK, j * p.nc_h + static_cast<int>(rank) * nch_half);
               }
               __syncwarp();
+              ++n_issued;
               if (++s == kStages) { s = 0; ph ^= 1; }
             }
           }
@@ -873,7 +882,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     for (int pt = kg; pt < n_ptiles; pt += p.KG) ++n_mine;
 
     if (warp == kMegaTmaWarp) {
-      int s = 0;
+      int s = 0, n_issued = 0;
       uint32_t ph = 0;
       long long w_ready = 0, w_empty = 0;
       const uint32_t sbase = smem_u32(smem);
@@ -885,7 +894,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         const int row0 = (pp * p.NS + slot) * 2 * kBM;
         for (int kb = 0; kb < 4; ++kb) {
           { PCNT_BEGIN(a); mbar_wait(&empty_bar[s], ph ^ 1); PCNT_END(a, w_empty); }
-          if (elect_one()) {
+          if ((p.dbg & 256) && n_issued >= kStages) {
+            if (leader && elect_one()) mbar_arrive(&full_bar[s]);
+          } else if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(&full_bar[s], stage_tx);
             const uint32_t sa = sbase + s * kCStageBytes;
             const int rr = row0 + kb * 64;
@@ -899,6 +910,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             }
           }
           __syncwarp();
+          ++n_issued;
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }

@@ -11,7 +11,7 @@ B, T, U, V, H, _ = WORKLOADS["target"]
 f, g, W, bias, y, fl, yl = synth(B, T, U, V, H, 1234, "cuda")
 fd, gd, Wd, bd, yd = f.cuda(), g.cuda(), W.cuda(), bias.cuda(), y.cuda()
 names = ["mma_loop_cyc", "mma_wait_full", "mma_wait_tempty", "mma_loop_ns"]
-for dbg, label in ((4, "all loads"), (4 | 8, "no A loads"), (4 | 16, "no B loads"), (4 | 8 | 16, "no loads")):
+for dbg, label in ((4, "all loads"), (4 | 8, "no A loads"), (4 | 16, "no B loads"), (4 | 256, "no loads after ring fill")):
     lib.rnnt_debug_set(b"gemm_dbg", dbg)
     for it in range(3):
         with torch.no_grad():

@@ -16,6 +16,6 @@ for dbg in (0, 1, 2, 3, 0):
         with torch.no_grad():
             loss = M.rnnt_joint_loss(fd, gd, Wd, bd, yd, fl, yl, V - 1)
         torch.cuda.synchronize()
-    kms = (ctypes.c_double * 8)(); kn = (ctypes.c_longlong * 8)()
-    lib.rnnt_debug_kernel_times(kms, kn, 8)
-    print(f"dbg={dbg}: " + "  ".join(f"{KCLASSES[i]}={kms[i]:.3f}ms/{kn[i]}" for i in range(8) if kn[i]), flush=True)
+    kms = (ctypes.c_double * 16)(); kn = (ctypes.c_longlong * 16)()
+    lib.rnnt_debug_kernel_times(kms, kn, 16)
+    print(f"dbg={dbg}: " + "  ".join(f"{KCLASSES[i]}={kms[i]:.3f}ms/{kn[i]}" for i in range(len(KCLASSES)) if kn[i]), flush=True)

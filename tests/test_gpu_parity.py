@@ -20,6 +20,17 @@ from oracle import rnnt_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=["persistent", "slab"], autouse=True)
+def kernel_path(request):
+    """Every test runs on both schedules of the C-ABI library: the persistent kernels (one forward launch, one
+    backward mega-kernel; the default) and the per-slab kernels (the general fallback)."""
+    from myrtlespeech_b200 import _lib
+    lib = _lib.load()
+    lib.rnnt_debug_set(b"path", 1 if request.param == "persistent" else 0)
+    yield request.param
+    lib.rnnt_debug_set(b"path", 1)
+
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-3
 
@@ -120,6 +131,29 @@ def test_subword_shape_multi_slab_matches_oracle():
     assert rel(got["loss"], ref["loss"]) < 1e-5
     for k in ("df", "dg", "dW", "db"):
         assert rel(got[k], ref[k]) < TOL, (k, rel(got[k], ref[k]))
+
+
+def test_ring_wraparound_many_tiles():
+    """208 tiles = 104 pair-tiles: more than producers x ring slots (50 x 2) of the backward mega-kernel, so every
+    producer reuses its slots and the consumers' `done` counters gate the reuse; ragged, V and H off the tile sizes."""
+    cfg = (11, 2, 200, 60, 130, 136, 129, True)
+    f, g, W, bias, y, fl, yl = make(*cfg)
+    got = run_cuda(f, g, W, bias, y, fl, yl, 129)
+    ref = O.rnnt_joint_loss(f.numpy(), g.numpy(), W.numpy(), bias.numpy(), y.numpy(), fl, yl, 129, faithful=True)
+    assert rel(got["loss"], ref["loss"]) < 1e-5
+    for k in ("df", "dg", "dW", "db"):
+        assert rel(got[k], ref[k]) < TOL, (k, rel(got[k], ref[k]))
+
+
+def test_repeated_calls_are_deterministic_in_loss_and_stable_in_grads():
+    """Back-to-back steps on the same workspace size: loss bit-identical, gradients equal up to atomics order."""
+    cfg = (12, 3, 50, 12, 70, 64, 69, True)
+    f, g, W, bias, y, fl, yl = make(*cfg)
+    a = run_cuda(f, g, W, bias, y, fl, yl, 69)
+    b = run_cuda(f, g, W, bias, y, fl, yl, 69)
+    assert np.array_equal(a["loss"], b["loss"])
+    for k in ("df", "dg", "dW", "db"):
+        assert rel(a[k], b[k]) < 1e-5, k
 
 
 def test_golden_fixtures():
