@@ -26,7 +26,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + ["-lcudart"]
+    prof = ["-DRNNT_PROFILE"] if os.environ.get("RNNT_PROFILE") == "1" else []
+    cmd = [nvcc] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + ["-lcudart"]
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

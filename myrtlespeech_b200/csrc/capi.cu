@@ -25,6 +25,9 @@ thread_local char g_err[512] = "";
 int g_slab_tiles_override = 0;
 int g_path = 1;  // 1 = persistent kernels (persist.cu), 0 = per-slab kernels (joint.cu)
 int g_ring_slots = 2;
+int g_cluster = 2;      // forward kernel: CTAs per cluster; 4 = two CTA pairs sharing W through TMA multicast
+                        // (measured slower: only 132 of the 148 SMs can host 4-clusters)
+int g_cluster_bwd = 2;  // backward mega-kernel: 4-clusters cannot all be co-resident (132 of 148 SMs), so pairs
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -236,6 +239,8 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "time_kernels")) g_time_kernels = value != 0;
   if (!strcmp(key, "gemm_dbg")) set_gemm_dbg(value);
   if (!strcmp(key, "path")) g_path = value;
+  if (!strcmp(key, "cluster") && (value == 2 || value == 4)) g_cluster = value;
+  if (!strcmp(key, "cluster_bwd") && (value == 2 || value == 4)) g_cluster_bwd = value;
   if (!strcmp(key, "ring_slots") && value >= 2 && value <= 4) g_ring_slots = value;
   if (!strcmp(key, "reset_launches")) for (int i = 0; i < K_NCLASS; ++i) g_launches[i] = 0;
 }
@@ -304,15 +309,22 @@ int rnnt_fused_forward(const void* f, const void* g, const void* W, const float*
   if (rc) return rc;
 
   if (g_path == 1) {
-    int n_ctas = sm_count() < kMaxPersistCtas ? sm_count() : kMaxPersistCtas;
-    n_ctas &= ~1;
+    const int csize = (nc % 32 == 0 && g_cluster == 4) ? 4 : 2;
+    int n_ctas = max_ctas_fwd_persist(csize);
+    if (n_ctas > kMaxPersistCtas) n_ctas = kMaxPersistCtas;
+    n_ctas = n_ctas / csize * csize;
     const int n_ptiles = (n_tiles + 1) / 2;
-    if (n_ctas > 2 * n_ptiles) n_ctas = 2 * n_ptiles;
+    const int need = (2 * n_ptiles + csize - 1) / csize * csize;
+    if (n_ctas > need) n_ctas = need;
     CUtensorMap tm_hs;
     rc = make_map(&tm_hs, w.at<void>(p.o_hs), H, static_cast<uint64_t>(kMaxPersistCtas) * 2 * kTileRows, H, 64, 128);
     if (rc) return rc;
+    if (csize == 4) {  // each CTA fetches a quarter of a W chunk
+      rc = make_map(&tm_w, W, H, V, H, 64, nc / 4);
+      if (rc) return rc;
+    }
     FwdPArgs pa{};
-    pa.L = L; pa.dbg = get_gemm_dbg(); pa.n_tiles_total = n_tiles; pa.V = V; pa.H = H; pa.nc = nc; pa.n_chunks = (V + nc - 1) / nc;
+    pa.L = L; pa.dbg = get_gemm_dbg(); pa.csize = csize; pa.n_tiles_total = n_tiles; pa.V = V; pa.H = H; pa.nc = nc; pa.n_chunks = (V + nc - 1) / nc;
     pa.k_blocks = (H + 63) / 64; pa.blank = blank; pa.Umax = d.Umax;
     pa.f = static_cast<const __nv_bfloat16*>(f); pa.g = static_cast<const __nv_bfloat16*>(g);
     pa.hscratch = w.at<__nv_bfloat16>(p.o_hs);
@@ -362,20 +374,25 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
   KLAUNCH(K_MISC, s, launch_transpose_w(static_cast<const __nv_bfloat16*>(W), w.at<__nv_bfloat16>(p.o_wt), V, H, p.Vp, s));
 
   const int nc_v = chunk_cols(V), nc_h = chunk_cols(H);
-  if (g_path == 1 && p.mega_ok && sm_count() >= kMaxPersistCtas) {
+  if (g_path == 1 && p.mega_ok && max_ctas_bwd_mega(2) >= 2 * (p.P + p.C)) {
     const uint64_t ring_rows = static_cast<uint64_t>(p.P) * p.NS * 2 * kTileRows;
+    // 4-clusters need both roles to start on a cluster boundary and both W chunk widths to split into quarters
+    const int csize = (g_cluster_bwd == 4 && p.P % 2 == 0 && p.C % 2 == 0 && nc_v % 32 == 0 && nc_h % 32 == 0 &&
+                       max_ctas_bwd_mega(4) >= 2 * (p.P + p.C)) ? 4 : 2;
+    const int wdiv = csize == 4 ? 4 : 2;
     CUtensorMap tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st;
     if ((rc = make_map(&tm_dz_st, w.at<void>(p.o_dzring), p.Vp, ring_rows, p.Vp, 64, 32))) return rc;
     if ((rc = make_map(&tm_h, w.at<void>(p.o_hring), H, ring_rows, H, 64, 128))) return rc;
-    if ((rc = make_map(&tm_w, W, H, V, H, 64, nc_v / 2))) return rc;
+    if ((rc = make_map(&tm_w, W, H, V, H, 64, nc_v / wdiv))) return rc;
     if ((rc = make_map(&tm_dz, w.at<void>(p.o_dzring), p.Vp, ring_rows, p.Vp, 64, 128))) return rc;
-    if ((rc = make_map(&tm_wt, w.at<void>(p.o_wt), p.Vp, H, p.Vp, 64, nc_h / 2))) return rc;
+    if ((rc = make_map(&tm_wt, w.at<void>(p.o_wt), p.Vp, H, p.Vp, 64, nc_h / wdiv))) return rc;
     if ((rc = make_map(&tm_dz_mn, w.at<void>(p.o_dzring), p.Vp, ring_rows, p.Vp, 64, 64))) return rc;
     if ((rc = make_map(&tm_h_mn, w.at<void>(p.o_hring), H, ring_rows, H, 64, 64))) return rc;
     const size_t n_flags = static_cast<size_t>(kMaxPersistCtas / 2) * kMaxRingSlots;
     CUDA_TRY(cudaMemsetAsync(w.at<unsigned>(p.o_flags), 0, sizeof(unsigned) * 2 * n_flags, s));
     BwdPArgs a{};
-    a.L = L; a.dbg = get_gemm_dbg(); a.n_tiles_total = n_tiles; a.V = V; a.H = H; a.Vp = p.Vp;
+    a.L = L; a.dbg = get_gemm_dbg(); a.csize = csize; a.cons_share = (csize == 4 && p.n_vt % 2 == 0) ? 1 : 0;
+    a.n_tiles_total = n_tiles; a.V = V; a.H = H; a.Vp = p.Vp;
     a.nc_v = nc_v; a.n_chunks_v = (V + nc_v - 1) / nc_v; a.kb_h = (H + 63) / 64;
     a.nc_h = nc_h; a.n_chunks_h = (H + nc_h - 1) / nc_h; a.kb_v = p.Vp / 64;
     a.blank = blank; a.Umax = d.Umax;

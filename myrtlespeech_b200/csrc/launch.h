@@ -89,6 +89,7 @@ constexpr int kMaxRingSlots = 4;
 struct FwdPArgs {
   Lattice L;
   int dbg;
+  int csize;                  // CTAs per cluster: 2 (one CTA pair) or 4 (two pairs, W multicast)
   int n_tiles_total;
   int V, H;
   int nc, n_chunks, k_blocks;
@@ -106,12 +107,15 @@ struct FwdPArgs {
 void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
                         cudaStream_t s);
 int smem_bytes_fwd_persist();
+int max_ctas_fwd_persist(int csize);
 int read_persist_prof(unsigned long long* out, int n);
 int get_gemm_dbg();
 
 struct BwdPArgs {
   Lattice L;
   int dbg;
+  int csize;                   // CTAs per cluster (2 or 4)
+  int cons_share;              // 4-clusters of consumers share their h boxes (n_vt even)
   int n_tiles_total;
   int V, H, Vp;
   int nc_v, n_chunks_v, kb_h;  // dz pass: N chunks over V, k-blocks over H
@@ -142,6 +146,7 @@ void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUt
                      const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, const CUtensorMap& tm_dz_st,
                      const BwdPArgs& a, int n_ctas, cudaStream_t s);
 int smem_bytes_bwd_mega();
+int max_ctas_bwd_mega(int csize);
 
 void set_gemm_dbg(int v);
 int read_gemm_prof(unsigned long long* out, int n);

@@ -35,7 +35,8 @@ constexpr int kMaxBiasCols = 2048;
 // warps, so the latency-critical single-issuer warps (TMA producer, MMA issuer) get the highest ids of their
 // sub-partitions; epilogue warps must satisfy (warp id % 4) == TMEM lane quadrant.
 //   forward: 0..3 epilogue, 4..7 hgen, 8 TMA, 9 MMA (+ TMEM alloc)
-//   mega   : 0..3 epilogue set 0, 4..7 epilogue set 1, 8..11 hgen, 12 TMA, 13 MMA (+ TMEM alloc)
+//   mega   : 0..3 epilogue set 0, 4..7 epilogue set 1, 10, 11, 14, 15 hgen (sub-partitions 2 and 3 only, away from
+//            the two issuer warps), 12 TMA, 13 MMA (+ TMEM alloc); 8, 9 idle
 constexpr int kFwdTmaWarp = 8, kFwdMmaWarp = 9;
 constexpr int kMegaTmaWarp = 12, kMegaMmaWarp = 13;
 
@@ -49,8 +50,15 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// The counters cost ~10 instructions per k-block on the single-thread issue paths, so they are compiled in only
+// with -DRNNT_PROFILE (RNNT_PROFILE=1 python -m myrtlespeech_b200.build --force).
+#ifdef RNNT_PROFILE
 #define PCNT_BEGIN(var) long long var##_t0 = 0; if (p.dbg & 4) var##_t0 = clock64()
 #define PCNT_END(var, acc) do { if (p.dbg & 4) acc += clock64() - var##_t0; } while (0)
+#else
+#define PCNT_BEGIN(var) do { } while (0)
+#define PCNT_END(var, acc) do { } while (0)
+#endif
 
 __device__ __forceinline__ float pick32(const float (&v)[32], int idx) {
   float r = v[0];
@@ -63,11 +71,47 @@ __device__ __forceinline__ void st_cg_u4(void* p, uint4 v) {
   asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+// mbarrier / commit helpers on precomputed shared-window addresses (the issue loops keep running addresses
+// instead of re-deriving them from the stage index every k-block)
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void umma_commit_pair_a(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
 // tma_load_2d_pair with the destination given as a shared-window address
 __device__ __forceinline__ void tma_load_2d_pair_a(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Multicast variant: the box lands at the same smem offset of every CTA in `mask`, and (cta_group::2) the bytes
+// are credited to the full barrier of each destination CTA's pair leader (verified: scripts/micro/mcast_test.cu).
+__device__ __forceinline__ void tma_load_2d_pair_mcast(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                       uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
 // generic-proxy global writes -> visible to later async-proxy (TMA) reads
@@ -146,16 +190,25 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  // Cluster of 2 (one CTA pair) or 4 (two pairs that share every W k-block through TMA multicast).
+  const uint32_t rank4 = cluster_ctarank();
+  const uint32_t rank = rank4 & 1;            // rank inside the cta_group::2 pair
+  const uint32_t cpair = rank4 >> 1;          // pair inside the cluster
   const bool leader = rank == 0;
+  const bool quad = p.csize == 4;
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * cpair));   // both CTAs of this pair
+  const uint16_t all_mask = quad ? 0xF : 0x3;                            // every CTA of the cluster
   const int pair = blockIdx.x >> 1;
   const int n_pairs = gridDim.x >> 1;
   const int n_ptiles = (p.n_tiles_total + 1) >> 1;
+  // Both pairs of a 4-cluster run the same number of iterations (they fill each other's B stages); a pair whose
+  // pair-tile index runs past the end processes a ghost tile whose results are discarded.
+  const int pt_first = quad ? (pair & ~1) : pair;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_a);
     prefetch_tmap(&tm_b);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], quad ? 2 : 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8);
       mbar_init(&hfull_bar[i], kHgenThreads); mbar_init(&hempty_bar[i], 1);
@@ -185,7 +238,7 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       uint32_t ph = 0;
       long long w_hfull = 0, w_empty = 0;
       const uint32_t sbase = smem_u32(stage_base);
-      for (int pt = pair; pt < n_ptiles; pt += n_pairs, ++it) {
+      for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += n_pairs, pf += n_pairs, ++it) {
         const int hb = it & 1;
         { PCNT_BEGIN(a); mbar_wait(&hfull_bar[hb], (it >> 1) & 1); PCNT_END(a, w_hfull); }
         for (int j = 0; j < p.n_chunks; ++j) {
@@ -199,8 +252,14 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
               if (leader) { if (tx) mbar_arrive_expect_tx(&full_bar[s], 2 * tx); else mbar_arrive(&full_bar[s]); }
               const uint32_t sa = sbase + s * kStageBytes;
               if (!(p.dbg & 8)) tma_load_2d_pair_a(sa, &tm_a, &full_bar[s], k * kBK, a_row0 + hb * kBM);
-              if (!(p.dbg & 16))
-                tma_load_2d_pair_a(sa + kAStage, &tm_b, &full_bar[s], k * kBK, j * p.nc + static_cast<int>(rank) * nc_half);
+              if (!(p.dbg & 16)) {
+                if (quad)   // this CTA fetches one quarter of the chunk and multicasts it to its twin in the other pair
+                  tma_load_2d_pair_mcast(sa + kAStage + cpair * (b_bytes >> 1), &tm_b, &full_bar[s], k * kBK,
+                                         j * p.nc + static_cast<int>(rank) * nc_half + static_cast<int>(cpair) * (nc_half >> 1),
+                                         static_cast<uint16_t>((1u << rank) | (1u << (rank + 2))));
+                else
+                  tma_load_2d_pair_a(sa + kAStage, &tm_b, &full_bar[s], k * kBK, j * p.nc + static_cast<int>(rank) * nc_half);
+              }
             }
             __syncwarp();
             ++n_issued;
@@ -218,39 +277,42 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     // floor (scripts/micro/mma_loop.cu: 626-1200 cyc/k-block diverged, 515 converged + poll-ahead).
     if (leader) {
       const uint32_t idesc = make_idesc_bf16(2 * kBM, p.nc, false, false);
-      const uint32_t sbase = smem_u32(stage_base);
+      // running stage state: descriptor of the stage's A tile (B = A + 16 KB), full / empty barrier addresses
+      const uint64_t ad0 = make_smem_desc_sw128(smem_u32(stage_base), 16, 1024);
+      const uint32_t fb0 = smem_u32(&full_bar[0]), eb0 = smem_u32(&empty_bar[0]);
+      uint64_t ad = ad0;
+      uint32_t fb = fb0, eb = eb0;
       int s = 0, gc = 0, it = 0;
       uint32_t ph = 0;
       bool ready = false;
       long long w_full = 0, w_tempty = 0;
       const long long c_begin = clock64();
       const unsigned long long ns_begin = gtimer_ns();
-      for (int pt = pair; pt < n_ptiles; pt += n_pairs, ++it) {
+      for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += n_pairs, pf += n_pairs, ++it) {
         for (int j = 0; j < p.n_chunks; ++j, ++gc) {
           const int buf = gc & 1;
           { PCNT_BEGIN(a); mbar_wait(&tempty_bar[buf], ((gc >> 1) & 1) ^ 1); PCNT_END(a, w_tempty); }
           const uint32_t d_tmem = tmem_base + buf * kNCmax;
           const bool last_chunk = j == p.n_chunks - 1;
           for (int k = 0; k < p.k_blocks; ++k) {
-            if (!ready) { PCNT_BEGIN(a); mbar_wait(&full_bar[s], ph); PCNT_END(a, w_full); }
+            if (!ready) { PCNT_BEGIN(a); mbar_wait_a(fb, ph); PCNT_END(a, w_full); }
             tc_fence_after();
-            const uint32_t a_addr = sbase + s * kStageBytes;
-            const uint64_t ad = make_smem_desc_sw128(a_addr, 16, 1024);
-            const uint64_t bd = make_smem_desc_sw128(a_addr + kAStage, 16, 1024);
+            const uint64_t bd = ad + (kAStage >> 4);
             const bool last_k = k == p.k_blocks - 1;
             if (elect_one()) {
 #pragma unroll
               for (int kk = 0; kk < kBK / 16; ++kk)
                 umma_bf16_pair(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-              umma_commit_pair(&empty_bar[s], 3);
+              umma_commit_pair_a(eb, all_mask);   // the stage is free once BOTH pairs have consumed it
               if (last_k) {
-                umma_commit_pair(&tfull_bar[buf], 3);
-                if (last_chunk) umma_commit_pair(&hempty_bar[it & 1], 3);  // scratch tile fully consumed
+                umma_commit_pair(&tfull_bar[buf], pair_mask);
+                if (last_chunk) umma_commit_pair(&hempty_bar[it & 1], pair_mask);  // scratch tile fully consumed
               }
             }
             __syncwarp();
-            if (++s == kStages) { s = 0; ph ^= 1; }
-            ready = mbar_try_wait(&full_bar[s], ph);  // poll ahead: the next wait is off the critical path
+            if (++s == kStages) { s = 0; ph ^= 1; ad = ad0; fb = fb0; eb = eb0; }
+            else { ad += kStageBytes >> 4; fb += 8; eb += 8; }
+            ready = mbar_try_wait_a(fb, ph);  // poll ahead: the next wait is off the critical path
           }
         }
       }
@@ -263,11 +325,11 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     }
   } else if (warp < 4) {
     // ------------------------------- epilogue ------------------------------------
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;
+    const int lq = warp & 3;                // TMEM lane quadrant
+    const int r = lq * 32 + lane;
     const int et = warp * 32 + lane;
     const int dt = r >> 3, du = r & 7;
-    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(lq * 32) << 16);
     const int ncols = p.n_chunks * p.nc;
     for (int c = et; c < ncols; c += kEpiThreads)
       sbias[c] = (c < p.V) ? (p.bias ? p.bias[c] * kLog2e : 0.0f) : -INFINITY;
@@ -275,7 +337,7 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
     int gc = 0;
     long long busy = 0;
-    for (int pt = pair; pt < n_ptiles; pt += n_pairs) {
+    for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += n_pairs, pf += n_pairs) {
       const int tile = 2 * pt + static_cast<int>(rank);
       const bool ghost = tile >= p.n_tiles_total;
       const TileInfo ti = decode_tile(p.L, ghost ? p.n_tiles_total - 1 : tile);
@@ -335,7 +397,7 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     __nv_bfloat16* my_scratch = p.hscratch + static_cast<size_t>(a_row0) * p.H;
     int it = 0;
     long long busy = 0;
-    for (int pt = pair; pt < n_ptiles; pt += n_pairs, ++it) {
+    for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += n_pairs, pf += n_pairs, ++it) {
       const int hb = it & 1;
       const int tile = 2 * pt + static_cast<int>(rank);
       mbar_wait(&hempty_bar[hb], ((it >> 1) & 1) ^ 1);
@@ -395,6 +457,9 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* ptr) {
 __device__ __forceinline__ void red_release_gpu_add_u32(unsigned* ptr, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_gpu_add_u32(unsigned* ptr, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void wait_counter_ge(const unsigned* ptr, unsigned target) {
   unsigned spins = 0;
   while (ld_acquire_gpu_u32(ptr) < target) {
@@ -411,7 +476,7 @@ __device__ __forceinline__ void tma_store_wait_all1() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-constexpr int kMegaThreads = 448;  // 14 warps, roles above
+constexpr int kMegaThreads = 512;  // 16 warps, roles above (warps 8, 9 idle)
 
 __global__ void __launch_bounds__(kMegaThreads, 1)
 bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
@@ -434,16 +499,25 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  // Cluster of 2 (one CTA pair) or 4 (two pairs of the same role that share an operand through TMA multicast:
+  // producers share every W / W^T k-block, consumers of one V-block pair share every h k-block).
+  const uint32_t rank4 = cluster_ctarank();
+  const uint32_t rank = rank4 & 1;            // rank inside the cta_group::2 pair
+  const uint32_t cpair = rank4 >> 1;          // pair inside the cluster
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
   const int n_ptiles = (p.n_tiles_total + 1) >> 1;
   const bool is_producer = pair < p.P;
+  const bool lockstep = p.csize == 4 && (is_producer || p.cons_share);   // this cluster's two pairs run in lockstep
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * cpair));
+  const uint16_t all_mask = lockstep ? 0xF : pair_mask;
+  const uint16_t twin_mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));
+  const int pt_first = lockstep ? (pair & ~1) : pair;   // lockstep: both pairs iterate while the first one has work
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_h); prefetch_tmap(&tm_w); prefetch_tmap(&tm_dz);
     prefetch_tmap(&tm_wt); prefetch_tmap(&tm_dz_mn); prefetch_tmap(&tm_h_mn); prefetch_tmap(&tm_dz_st);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], lockstep ? 2 : 1); }
     // producers: 8 epilogue warps per CTA; consumers: 4 flush warps per CTA never arrive on tempty
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }
     for (int i = 0; i < kMaxNS; ++i) { mbar_init(&hfull_bar[i], kHgenThreads); mbar_init(&hfree_bar[i], 8); }
@@ -478,7 +552,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         uint32_t ph = 0;
         long long w_hfull = 0, w_empty = 0, w_dzr = 0;
         const uint32_t sbase = smem_u32(stage_base);
-        for (int pt = pair; pt < n_ptiles; pt += p.P, ++it) {
+        for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P, ++it) {
           const int slot = it % p.NS, use = it / p.NS;
           const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
           { PCNT_BEGIN(a); mbar_wait(&hfull_bar[slot], use & 1); PCNT_END(a, w_hfull); }
@@ -491,7 +565,12 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * (kAStage + bv_bytes));
                 const uint32_t sa = sbase + s * kStageBytes;
                 tma_load_2d_pair_a(sa, &tm_h, &full_bar[s], k * kBK, ring_row);
-                tma_load_2d_pair_a(sa + kAStage, &tm_w, &full_bar[s], k * kBK, j * p.nc_v + static_cast<int>(rank) * ncv_half);
+                if (lockstep)
+                  tma_load_2d_pair_mcast(sa + kAStage + cpair * (bv_bytes >> 1), &tm_w, &full_bar[s], k * kBK,
+                                         j * p.nc_v + static_cast<int>(rank) * ncv_half + static_cast<int>(cpair) * (ncv_half >> 1),
+                                         twin_mask);
+                else
+                  tma_load_2d_pair_a(sa + kAStage, &tm_w, &full_bar[s], k * kBK, j * p.nc_v + static_cast<int>(rank) * ncv_half);
               }
               __syncwarp();
               ++n_issued;
@@ -516,7 +595,12 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * (kAStage + bh_bytes));
                 const uint32_t sa = sbase + s * kStageBytes;
                 tma_load_2d_pair_a(sa, &tm_dz, &full_bar[s], k * kBK, ring_row);
-                tma_load_2d_pair_a(sa + kAStage, &tm_wt, &full_bar[s], k * kBK, j * p.nc_h + static_cast<int>(rank) * nch_half);
+                if (lockstep)
+                  tma_load_2d_pair_mcast(sa + kAStage + cpair * (bh_bytes >> 1), &tm_wt, &full_bar[s], k * kBK,
+                                         j * p.nc_h + static_cast<int>(rank) * nch_half + static_cast<int>(cpair) * (nch_half >> 1),
+                                         twin_mask);
+                else
+                  tma_load_2d_pair_a(sa + kAStage, &tm_wt, &full_bar[s], k * kBK, j * p.nc_h + static_cast<int>(rank) * nch_half);
               }
               __syncwarp();
               ++n_issued;
@@ -533,14 +617,17 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       if (leader) {
         const uint32_t idesc_v = make_idesc_bf16(2 * kBM, p.nc_v, false, false);
         const uint32_t idesc_h = make_idesc_bf16(2 * kBM, p.nc_h, false, false);
-        const uint32_t sbase = smem_u32(stage_base);
+        const uint64_t ad0 = make_smem_desc_sw128(smem_u32(stage_base), 16, 1024);
+        const uint32_t fb0 = smem_u32(&full_bar[0]), eb0 = smem_u32(&empty_bar[0]);
+        uint64_t ad = ad0;
+        uint32_t fb = fb0, eb = eb0;
         int s = 0, gc = 0;
         uint32_t ph = 0;
         bool ready = false;
         long long w_full = 0, w_tempty = 0;
         const long long c_begin = clock64();
         const unsigned long long ns_begin = gtimer_ns();
-        for (int pt = pair; pt < n_ptiles; pt += p.P) {
+        for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P) {
           for (int pass = 0; pass < 2; ++pass) {
             const int n_chunks = pass == 0 ? p.n_chunks_v : p.n_chunks_h;
             const int k_blocks = pass == 0 ? p.kb_h : p.kb_v;
@@ -550,22 +637,21 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
               { PCNT_BEGIN(a); mbar_wait(&tempty_bar[buf], ((gc >> 1) & 1) ^ 1); PCNT_END(a, w_tempty); }
               const uint32_t d_tmem = tmem_base + buf * kNCmax;
               for (int k = 0; k < k_blocks; ++k) {
-                if (!ready) { PCNT_BEGIN(a); mbar_wait(&full_bar[s], ph); PCNT_END(a, w_full); }
+                if (!ready) { PCNT_BEGIN(a); mbar_wait_a(fb, ph); PCNT_END(a, w_full); }
                 tc_fence_after();
-                const uint32_t a_addr = sbase + s * kStageBytes;
-                const uint64_t ad = make_smem_desc_sw128(a_addr, 16, 1024);
-                const uint64_t bd = make_smem_desc_sw128(a_addr + kAStage, 16, 1024);
+                const uint64_t bd = ad + (kAStage >> 4);
                 const bool last_k = k == k_blocks - 1;
                 if (elect_one()) {
 #pragma unroll
                   for (int kk = 0; kk < kBK / 16; ++kk)
                     umma_bf16_pair(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-                  umma_commit_pair(&empty_bar[s], 3);
-                  if (last_k) umma_commit_pair(&tfull_bar[buf], 3);
+                  umma_commit_pair_a(eb, all_mask);
+                  if (last_k) umma_commit_pair(&tfull_bar[buf], pair_mask);
                 }
                 __syncwarp();
-                if (++s == kStages) { s = 0; ph ^= 1; }
-                ready = mbar_try_wait(&full_bar[s], ph);
+                if (++s == kStages) { s = 0; ph ^= 1; ad = ad0; fb = fb0; eb = eb0; }
+                else { ad += kStageBytes >> 4; fb += 8; eb += 8; }
+                ready = mbar_try_wait_a(fb, ph);
               }
             }
           }
@@ -605,7 +691,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       n_my_sub = n_my_sub < 0 ? 0 : (n_my_sub > 2 ? 2 : n_my_sub);
 
       int gc = 0, it = 0;
-      for (int pt = pair; pt < n_ptiles; pt += p.P, ++it) {
+      for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P, ++it) {
         const int slot = it % p.NS, use = it / p.NS;
         const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
         const int tile = 2 * pt + static_cast<int>(rank);
@@ -840,11 +926,11 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           if (lane == 0) mbar_arrive(&hfree_bar[slot]);
         }
       }
-    } else if (warp < 12) {
-      // ------------------------------- hgen (warps 8..11) ----------------------------
-      const int ht = threadIdx.x - 256;
+    } else if (warp >= 10) {
+      // ------------------------------- hgen (warps 10, 11, 14, 15) --------------------
+      const int ht = ((warp & 1) + ((warp >> 2) & 1) * 2) * 32 + lane;   // 10->0, 11->1, 14->2, 15->3
       int it = 0;
-      for (int pt = pair; pt < n_ptiles; pt += p.P, ++it) {
+      for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P, ++it) {
         const int slot = it % p.NS, use = it / p.NS;
         const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
         const int tile = 2 * pt + static_cast<int>(rank);
@@ -872,7 +958,8 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     const int c = pair - p.P;
     const int kg = c / p.n_out;
     const int otile = c - kg * p.n_out;
-    const int vt = otile / p.n_ht, hn = otile - vt * p.n_ht;
+    // adjacent consumer pairs take adjacent V-blocks of the same H-block, so a 4-cluster shares its h boxes
+    const int hn = otile / p.n_vt, vt = otile - hn * p.n_vt;
     const bool two = (p.H - hn * 512) > 256;
     const int v0 = vt * 256 + static_cast<int>(rank) * 128;    // this CTA's 128 V rows of the pair's 256
     const int hx0 = hn * 512 + static_cast<int>(rank) * 128;   // this CTA's half of accumulator X's 256 H columns
@@ -902,11 +989,22 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             const int rr = row0 + kb * 64;
 #pragma unroll
             for (int q = 0; q < 2; ++q) tma_load_2d_pair_a(sa + q * 8192, &tm_dz_mn, &full_bar[s], v0 + q * 64, rr);
+            if (!lockstep) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) tma_load_2d_pair_a(sa + 16384 + q * 8192, &tm_h_mn, &full_bar[s], hx0 + q * 64, rr);
-            if (two) {
+              for (int q = 0; q < 2; ++q) tma_load_2d_pair_a(sa + 16384 + q * 8192, &tm_h_mn, &full_bar[s], hx0 + q * 64, rr);
+              if (two) {
 #pragma unroll
-              for (int q = 0; q < 2; ++q) tma_load_2d_pair_a(sa + 32768 + q * 8192, &tm_h_mn, &full_bar[s], hy0 + q * 64, rr);
+                for (int q = 0; q < 2; ++q) tma_load_2d_pair_a(sa + 32768 + q * 8192, &tm_h_mn, &full_bar[s], hy0 + q * 64, rr);
+              }
+            } else if (two) {      // pair 0 of the cluster fetches the X boxes, pair 1 the Y boxes; both multicast
+              const uint32_t off = cpair ? 32768u : 16384u;
+              const int hc = cpair ? hy0 : hx0;
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                tma_load_2d_pair_mcast(sa + off + q * 8192, &tm_h_mn, &full_bar[s], hc + q * 64, rr, twin_mask);
+            } else {
+              tma_load_2d_pair_mcast(sa + 16384 + cpair * 8192, &tm_h_mn, &full_bar[s], hx0 + static_cast<int>(cpair) * 64, rr,
+                                     twin_mask);
             }
           }
           __syncwarp();
@@ -918,7 +1016,11 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     } else if (warp == kMegaMmaWarp) {
       if (leader) {
         const uint32_t idesc = make_idesc_bf16(256, 256, true, true);
-        const uint32_t sbase = smem_u32(smem);
+        // MN-major SW128: lbo = 8192 (next 64-element M/N group = next TMA box), sbo = 1024 (next 8 k rows)
+        const uint64_t ad0 = make_smem_desc_sw128(smem_u32(smem), 8192, 1024);
+        const uint32_t fb0 = smem_u32(&full_bar[0]), eb0 = smem_u32(&empty_bar[0]);
+        uint64_t ad = ad0;
+        uint32_t fb = fb0, eb = eb0;
         int s = 0;
         uint32_t ph = 0;
         bool ready = false;
@@ -928,32 +1030,30 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         const unsigned long long ns_begin = gtimer_ns();
         for (int pt = kg; pt < n_ptiles; pt += p.KG) {
           const int pp = pt % p.P, it = pt / p.P;
-          const int slot = it % p.NS;
+          unsigned* done_ptr = p.done + pp * p.NS + it % p.NS;
           for (int kb = 0; kb < 4; ++kb) {
-            if (!ready) { PCNT_BEGIN(a); mbar_wait(&full_bar[s], ph); PCNT_END(a, w_full); }
+            if (!ready) { PCNT_BEGIN(a); mbar_wait_a(fb, ph); PCNT_END(a, w_full); }
             tc_fence_after();
-            const uint32_t a_addr = sbase + s * kCStageBytes;
-            // MN-major SW128: lbo = 8192 (next 64-element M/N group = next TMA box), sbo = 1024 (next 8 k rows)
-            const uint64_t ad = make_smem_desc_sw128(a_addr, 8192, 1024);
-            const uint64_t bx = make_smem_desc_sw128(a_addr + 16384, 8192, 1024);
-            const uint64_t by = make_smem_desc_sw128(a_addr + 32768, 8192, 1024);
+            const uint64_t bx = ad + (16384 >> 4), by = ad + (32768 >> 4);
             if (elect_one()) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {   // +2048 B per 16 rows of K -> +128 in the encoded address field
                 umma_bf16_pair(tmem_base, ad + 128 * kk, bx + 128 * kk, idesc, (acc | kk) != 0 ? 1u : 0u);
                 if (two) umma_bf16_pair(tmem_base + 256, ad + 128 * kk, by + 128 * kk, idesc, (acc | kk) != 0 ? 1u : 0u);
               }
-              umma_commit_pair(&empty_bar[s], 3);
-              // the slot's rows have landed in smem (both CTAs' bytes are counted on this barrier)
-              if (kb == 3) red_release_gpu_add_u32(p.done + pp * p.NS + slot, 1u);
+              umma_commit_pair_a(eb, all_mask);
+              // the slot's rows have landed in smem (both CTAs' bytes are counted on this barrier); this thread has
+              // written nothing the producer must see, so a relaxed increment is enough
+              if (kb == 3) red_relaxed_gpu_add_u32(done_ptr, 1u);
             }
             __syncwarp();
             acc = 1;
-            if (++s == kStages) { s = 0; ph ^= 1; }
-            ready = mbar_try_wait(&full_bar[s], ph);
+            if (++s == kStages) { s = 0; ph ^= 1; ad = ad0; fb = fb0; eb = eb0; }
+            else { ad += kCStageBytes >> 4; fb += 8; eb += 8; }
+            ready = mbar_try_wait_a(fb, ph);
           }
         }
-        if (n_mine > 0 && elect_one()) umma_commit_pair(&tfull_bar[0], 3);
+        if (n_mine > 0 && elect_one()) umma_commit_pair(&tfull_bar[0], pair_mask);
         __syncwarp();
         if ((p.dbg & 4) && lane == 0) {
           g_pprof[blockIdx.x * 8 + 0] = clock64() - c_begin;
@@ -1009,6 +1109,26 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 }  // namespace
 
 int smem_bytes_fwd_persist() { return kFwdSmem; }
+
+// Largest number of CTAs of the forward kernel that are co-resident for this cluster size (GPCs whose SM count is
+// not a multiple of the cluster size strand SMs: 148 CTAs fit as pairs, only 132 as 4-clusters on this B200).
+int max_ctas_fwd_persist(int csize) {
+  static int cached[5] = {0, 0, 0, 0, 0};
+  if (cached[csize]) return cached[csize];
+  cudaFuncSetAttribute(fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(csize * 64);
+  cfg.blockDim = dim3(kPThreads);
+  cfg.dynamicSmemBytes = kFwdSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, fwd_persist_kernel, &cfg) != cudaSuccess || n <= 0) n = 148 / csize;
+  cached[csize] = n * csize;
+  return cached[csize];
+}
 int read_persist_prof(unsigned long long* out, int n) {
   if (n > 160 * 8) n = 160 * 8;
   return cudaMemcpyFromSymbol(out, g_pprof, sizeof(unsigned long long) * n) == cudaSuccess ? n : -1;
@@ -1028,13 +1148,33 @@ void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w,
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = a.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, fwd_persist_kernel, tm_hscratch, tm_w, a);
 }
 
 
 int smem_bytes_bwd_mega() { return kMegaSmem; }
+
+// Co-resident CTA capacity of the mega-kernel for a cluster size (its CTAs wait on one another: every CTA of the
+// grid must be resident at once).
+int max_ctas_bwd_mega(int csize) {
+  static int cached[5] = {0, 0, 0, 0, 0};
+  if (cached[csize]) return cached[csize];
+  cudaFuncSetAttribute(bwd_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(csize * 64);
+  cfg.blockDim = dim3(kMegaThreads);
+  cfg.dynamicSmemBytes = kMegaSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, bwd_mega_kernel, &cfg) != cudaSuccess || n <= 0) n = 0;
+  cached[csize] = n * csize;
+  return cached[csize];
+}
 
 void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUtensorMap& tm_dz, const CUtensorMap& tm_wt,
                      const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, const CUtensorMap& tm_dz_st,
@@ -1051,7 +1191,7 @@ void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUt
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = a.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, bwd_mega_kernel, tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a);
 }

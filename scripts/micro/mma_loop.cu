@@ -3,6 +3,8 @@
 // stretches a k-block from the 512-cycle floor to ~760 cycles.
 #include <cstdio>
 #include <cstdint>
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 #include "../../myrtlespeech_b200/csrc/ptx.cuh"
 using namespace rnnt;
@@ -17,9 +19,11 @@ struct Cfg {
   int chunk_kb;    // switch accumulator buffer + extra commit every chunk_kb k-blocks (0 = never)
   int epi;         // epilogue warps: 0 none, 1 tcgen05.ld the other buffer continuously
   int lean;        // 1: whole loop inside lane 0, incremental stage/phase, no per-iteration reconvergence; 2: + poll-ahead
+  int tma;         // producer issues real TMA loads (2 x 16 KB per k-block per CTA) instead of a plain arrive
+  int lsu;         // epilogue warps hammer shared memory: 1 = LDS.128 only, 2 = STS.128 + LDS.128
 };
 
-__global__ void __launch_bounds__(192, 1) mma_loop_kernel(Cfg c, long long* out_cycles) {
+__global__ void __launch_bounds__(192, 1) mma_loop_kernel(const __grid_constant__ CUtensorMap tm, Cfg c, long long* out_cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[8], empty_bar[8], done_bar, tfull_bar;
@@ -53,7 +57,26 @@ __global__ void __launch_bounds__(192, 1) mma_loop_kernel(Cfg c, long long* out_
   tc_fence_before(); __syncthreads(); cluster_sync_all(); tc_fence_after();
   const uint32_t tmem = tmem_slot;
   if (warp == 0) {
-    if (lane == 0 && c.use_full && rank == 0) {
+    if (c.tma) {
+      // both CTAs load their own boxes; bytes are credited to the leader's full barrier (as in the real kernels)
+      const uint32_t sbase = smem_u32(smem);
+      const int row0 = blockIdx.x * 256;
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < c.n_kb; ++it) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 4 * 16384);
+          const uint32_t sa = sbase + s * 32768;
+          const int col = (it & 15) * 64;
+          asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(sa), "l"(reinterpret_cast<uint64_t>(&tm)), "r"(smem_u32(&full_bar[s]) & kPeerBitMask), "r"(col), "r"(row0) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(sa + 16384), "l"(reinterpret_cast<uint64_t>(&tm)), "r"(smem_u32(&full_bar[s]) & kPeerBitMask), "r"(col), "r"(row0 + 128) : "memory");
+        }
+        __syncwarp();
+        if (++s == c.stages) { s = 0; ph ^= 1; }
+      }
+    } else if (lane == 0 && c.use_full && rank == 0) {
       for (int it = 0; it < c.n_kb; ++it) {
         const int s = it % c.stages;
         mbar_wait(&empty_bar[s], ((it / c.stages) & 1) ^ 1);
@@ -129,12 +152,28 @@ __global__ void __launch_bounds__(192, 1) mma_loop_kernel(Cfg c, long long* out_
         }
         __syncwarp();
       }
-      if (lane == 0) umma_commit_pair(&done_bar, 1);
+      if (lane == 0) umma_commit_pair(&done_bar, 3);
       __syncwarp();
       mbar_wait(&done_bar, 0);
       const long long t1 = clock64();
-      if (lane == 0) { out_cycles[blockIdx.x] = t1 - t0; stop_flag = 1; }
+      if (lane == 0) { out_cycles[blockIdx.x] = t1 - t0; }
+    } else {
+      mbar_wait(&done_bar, 0);   // the leader's last commit reaches both CTAs
     }
+    if (lane == 0) { stop_flag = 1; }
+  } else if (c.lsu) {
+    // shared-memory traffic generator in the 6 KB x 4 warps after the stage ring (no TMEM access)
+    uint4* region = reinterpret_cast<uint4*>(smem + 6 * 32768) + (warp - 2) * 256;   // 4 KB per warp
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    while (!stop_flag) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (c.lsu == 2) region[i * 32 + lane] = acc;
+        const uint4 v = region[((i + 1) & 7) * 32 + lane];
+        acc.x ^= v.x; acc.y += v.y; acc.z ^= v.z; acc.w += v.w;
+      }
+    }
+    if (acc.x == 0x12345678u) out_cycles[146] = acc.y;
   } else if (c.epi % 10) {
     // epilogue-like TMEM readers on buffer 1 (values irrelevant)
     const uint32_t lane_taddr = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
@@ -156,10 +195,25 @@ __global__ void __launch_bounds__(192, 1) mma_loop_kernel(Cfg c, long long* out_
 
 int main(int argc, char** argv) {
   long long* d_out; cudaMalloc(&d_out, sizeof(long long) * 148);
-  const int smem = 200 * 1024;
+  const int smem = 216 * 1024;
+  PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  { void* pp = nullptr; cudaDriverEntryPointQueryResult q;
+    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &pp, cudaEnableDefault, &q); enc = (PFN_cuTensorMapEncodeTiled_v12000)pp; }
+  const uint64_t cols = 1024, rows = 148ull * 256;
+  void* gbuf; cudaMalloc(&gbuf, cols * rows * 2); cudaMemset(gbuf, 0x3c, cols * rows * 2);
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {cols, rows}; cuuint64_t strides[1] = {cols * 2}; cuuint32_t box[2] = {64, 128}; cuuint32_t es[2] = {1, 1};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gbuf, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode failed\n"); return 1; }
   cudaFuncSetAttribute(mma_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   Cfg cfgs[] = {
-    {100000, 6, 1, 1, 3, 1, 16, 0, 3}, {100000, 6, 1, 1, 3, 1, 16, 10, 3}, {100000, 6, 1, 1, 3, 1, 16, 11, 3},
+    //  n_kb st full fence mask lanes chunk epi lean tma lsu
+    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 0, 0},
+    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 1, 0},
+    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 1, 1},
+    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 1, 2},
+    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 0, 2},
+    {20000, 4, 1, 1, 3, 1, 16, 10, 3, 1, 0},
   };
   for (auto& c : cfgs) {
     for (int grid : {148}) {
@@ -169,18 +223,18 @@ int main(int argc, char** argv) {
       lc.attrs = at; lc.numAttrs = 1;
       cudaMemset(d_out, 0, sizeof(long long) * 148);
       for (int rep = 0; rep < 2; ++rep) {
-        cudaError_t le = cudaLaunchKernelEx(&lc, mma_loop_kernel, c, d_out);
+        cudaError_t le = cudaLaunchKernelEx(&lc, mma_loop_kernel, tm, c, d_out);
         if (le != cudaSuccess) printf("launch error %s\n", cudaGetErrorString(le));
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
       }
       cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-      cudaEventRecord(e0); cudaLaunchKernelEx(&lc, mma_loop_kernel, c, d_out); cudaEventRecord(e1); cudaDeviceSynchronize();
+      cudaEventRecord(e0); cudaLaunchKernelEx(&lc, mma_loop_kernel, tm, c, d_out); cudaEventRecord(e1); cudaDeviceSynchronize();
       float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
       long long h[148]; cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
       long long mx = 0; for (int i = 0; i < grid; i += 2) if (h[i] > mx) mx = h[i];
-      printf("grid=%3d stages=%d full=%d fence=%d mask=%d all_lanes=%d chunk=%2d epi=%d lean=%d : %7.1f cyc/k-block (%5.1f per MMA)\n", grid,
-             c.stages, c.use_full, c.fence, c.mask, c.all_lanes, c.chunk_kb, c.epi, c.lean, (double)mx / c.n_kb, (double)mx / c.n_kb / 4);
+      printf("grid=%3d stages=%d tma=%d lsu=%d chunk=%2d epi=%d lean=%d : %7.1f cyc/k-block (%5.1f per MMA)\n", grid,
+             c.stages, c.tma, c.lsu, c.chunk_kb, c.epi, c.lean, (double)mx / c.n_kb, (double)mx / c.n_kb / 4);
       printf("    kernel %.3f ms -> %.1f ns per MMA, %.1f TFLOP/s chip, effective clock %.3f GHz\n", ms, ms * 1e6 / (c.n_kb * 4.0), 74.0 * c.n_kb * 4.0 * 2 * 256 * 256 * 16 / (ms * 1e-3) / 1e12, mx / (ms * 1e6));
       fflush(stdout);
     }
