@@ -71,46 +71,132 @@ class RNNTGreedyDecoder(torch.nn.Module):
         finally:
             model.train(was_training)
 
+    #: decode steps enqueued between two host checks of "is any utterance still active"
+    SYNC_EVERY = 32
+    #: replay one captured CUDA graph per decode step instead of ~20 eager launches (falls back to eager launches
+    #: if the prediction network cannot be captured)
+    USE_CUDA_GRAPH = True
+
     def _decode(self, f: torch.Tensor, lengths: torch.Tensor) -> List[List[int]]:
+        """All bookkeeping (current frame, symbols emitted at it, activity mask, emitted ids) lives on the
+        device and one decode step is a fixed sequence of in-place updates, so it is captured once as a CUDA graph
+        and replayed; the host only polls the activity mask every ``SYNC_EVERY`` steps.  The reference's greedy CTC
+        decoder pays one ``.item()`` sync per frame (``post_process/ctc_greedy_decoder.py:77-91``)."""
         model = self._model
         dev = model.joint.fc.weight.device
         B, T, H = f.shape
+        S = self.max_symbols_per_step
+        blank = self.blank_index
         fb = f.to(dev, torch.bfloat16).contiguous()
         Wb = model.joint.fc.weight.detach().to(torch.bfloat16).contiguous()
         bias = model.joint.fc.bias
         bias = None if bias is None else bias.detach().float().contiguous()
-        lens = lengths.to("cpu", torch.int64)
+        lens = lengths.to(dev, torch.int32)
         pred = model.prediction
 
-        g, hid = pred.step(None, None, B, dev)
-        out: List[List[int]] = [[] for _ in range(B)]
-        t_host = torch.zeros(B, dtype=torch.int64)          # current frame of each utterance
-        emitted = torch.zeros(B, dtype=torch.int64)          # symbols emitted at the current frame
-        active = t_host < lens
+        g0, hid0 = pred.step(None, None, B, dev)
+        g = g0.clone()
+        hid = _clone_hidden(hid0)
+        g16 = torch.empty(B, H, dtype=torch.bfloat16, device=dev)
+        cap = max(1, T * S)                                   # at most S symbols per frame
+        sym = torch.zeros(B, cap, dtype=torch.int32, device=dev)
+        n_sym = torch.zeros(B, dtype=torch.int64, device=dev)
+        t_cur = torch.zeros(B, dtype=torch.int32, device=dev)   # current frame of each utterance
+        emitted = torch.zeros(B, dtype=torch.int32, device=dev)  # symbols emitted at the current frame
+        active = t_cur < lens
         t_idx = torch.empty(B, dtype=torch.int32, device=dev)
         k_dev = torch.empty(B, dtype=torch.int32, device=dev)
-        while bool(active.any()):
-            t_idx.copy_(torch.where(active, t_host, torch.full_like(t_host, -1)).to(torch.int32))
-            greedy_joint_argmax(fb, g.to(torch.bfloat16).contiguous(), Wb, bias, t_idx, k_dev)
-            k = k_dev.cpu().to(torch.int64)
-            is_sym = active & (k != self.blank_index)
-            for b in torch.nonzero(is_sym).flatten().tolist():
-                out[b].append(int(k[b]))
-            if bool(is_sym.any()):
-                # advance the prediction network only where a symbol was emitted
-                g_new, hid_new = pred.step(k.clamp(min=0).to(dev), hid, B, dev)
-                m = is_sym.to(dev)
-                g = torch.where(m[:, None], g_new, g)
-                hid = _select_hidden(m, hid_new, hid)
-            emitted = torch.where(is_sym, emitted + 1, emitted)
-            advance = active & (~is_sym | (emitted >= self.max_symbols_per_step))
-            t_host = torch.where(advance, t_host + 1, t_host)
-            emitted = torch.where(advance, torch.zeros_like(emitted), emitted)
-            active = t_host < lens
-        return out
+        minus1 = torch.full((B,), -1, dtype=torch.int32, device=dev)
+        zero = torch.zeros(B, dtype=torch.int32, device=dev)
+
+        def step():
+            t_idx.copy_(torch.where(active, t_cur, minus1))
+            g16.copy_(g)
+            greedy_joint_argmax(fb, g16, Wb, bias, t_idx, k_dev)
+            is_sym = active & (k_dev != blank)
+            # append k to the rows that emitted (masked scatter at column n_sym)
+            col = n_sym.clamp(max=cap - 1).unsqueeze(1)
+            sym.scatter_(1, col, torch.where(is_sym, k_dev, sym.gather(1, col).squeeze(1)).unsqueeze(1))
+            n_sym.add_(is_sym)
+            # advance the prediction network only where a symbol was emitted (computed for all, selected by mask)
+            g_new, hid_new = pred.step(k_dev.clamp(min=0).long(), hid, B, dev)
+            g.copy_(torch.where(is_sym[:, None], g_new, g))
+            _update_hidden(is_sym, hid_new, hid)
+            em = torch.where(is_sym, emitted + 1, emitted)
+            advance = active & (~is_sym | (em >= S))
+            t_cur.add_(advance.to(torch.int32))
+            emitted.copy_(torch.where(advance, zero, em))
+            active.copy_(t_cur < lens)
+
+        graph = None
+        if self.USE_CUDA_GRAPH:
+            graph = _try_capture(step, (g, hid, sym, n_sym, t_cur, emitted, active))
+        n = 0
+        while True:
+            if n % self.SYNC_EVERY == 0 and not bool(active.any()):
+                break
+            n += 1
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+        sym_h, n_h = sym.cpu(), n_sym.cpu().tolist()
+        return [sym_h[b, : n_h[b]].tolist() for b in range(B)]
 
     def extra_repr(self) -> str:
         return f"blank_index={self.blank_index}, max_symbols_per_step={self.max_symbols_per_step}"
+
+
+def _clone_hidden(h):
+    if h is None:
+        return None
+    if isinstance(h, tuple):
+        return tuple(_clone_hidden(x) for x in h)
+    return h.clone()
+
+
+def _update_hidden(mask: torch.Tensor, new, old) -> None:
+    """In place: old <- where(mask, new, old) for every state tensor (stateless networks carry None)."""
+    if new is None or old is None:
+        return
+    if isinstance(new, tuple):
+        for n, o in zip(new, old):
+            _update_hidden(mask, n, o)
+        return
+    old.copy_(torch.where(mask[None, :, None], new, old))
+
+
+def _try_capture(step, state):
+    """Captures ``step`` as a CUDA graph.  The warm-up steps it needs run for real, so the state is snapshotted
+    before and restored afterwards.  Returns None if capture is not possible."""
+    def flat(x, out):
+        if x is None:
+            return out
+        if isinstance(x, tuple):
+            for y in x:
+                flat(y, out)
+            return out
+        out.append(x)
+        return out
+
+    tensors = flat(tuple(state), [])
+    saved = [t.clone() for t in tensors]
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+    except Exception:
+        graph = None
+        torch.cuda.synchronize()
+    for t, v in zip(tensors, saved):
+        t.copy_(v)
+    return graph
 
 
 def _select_hidden(mask: torch.Tensor, new, old):
