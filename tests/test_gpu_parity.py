@@ -145,6 +145,22 @@ def test_ring_wraparound_many_tiles():
         assert rel(got[k], ref[k]) < TOL, (k, rel(got[k], ref[k]))
 
 
+@pytest.mark.parametrize("shape", [
+    # B, T, U, V, H: role splits of the backward mega-kernel other than the 8-block x 3-group one
+    (2, 20, 5, 2048, 64),     # 8 V-blocks x 1 H-block (max V)
+    (2, 20, 5, 64, 1536),     # 1 V-block x 3 H-blocks, odd number of dW blocks (no consumer sharing)
+    (1, 9, 3, 2048, 3072),    # 48 dW blocks: more consumers than the split allows -> per-slab kernels
+], ids=lambda s: "V%d_H%d" % (s[3], s[4]))
+def test_wide_shapes(shape):
+    B, T, U, V, H = shape
+    f, g, W, bias, y, fl, yl = make(21, B, T, U, V, H, V - 1, True)
+    got = run_cuda(f, g, W, bias, y, fl, yl, V - 1)
+    ref = O.rnnt_joint_loss(f.numpy(), g.numpy(), W.numpy(), bias.numpy(), y.numpy(), fl, yl, V - 1, faithful=True)
+    assert rel(got["loss"], ref["loss"]) < 1e-5
+    for k in ("df", "dg", "dW", "db"):
+        assert rel(got[k], ref[k]) < TOL, (k, rel(got[k], ref[k]))
+
+
 def test_repeated_calls_are_deterministic_in_loss_and_stable_in_grads():
     """Back-to-back steps on the same workspace size: loss bit-identical, gradients equal up to atomics order."""
     cfg = (12, 3, 50, 12, 70, 64, 69, True)
