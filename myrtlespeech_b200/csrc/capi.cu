@@ -252,6 +252,7 @@ long long rnnt_debug_get(const char* key) {
     return n;
   }
   if (!strcmp(key, "n_classes")) return K_NCLASS;
+  if (!strcmp(key, "mega_cooperative")) return bwd_mega_cooperative();
   return -1;
 }
 

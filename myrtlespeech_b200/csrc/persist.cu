@@ -1176,10 +1176,14 @@ int max_ctas_bwd_mega(int csize) {
   return cached[csize];
 }
 
+static bool g_mega_cooperative = true;
+int bwd_mega_cooperative() { return g_mega_cooperative ? 1 : 0; }
+
 void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUtensorMap& tm_dz, const CUtensorMap& tm_wt,
                      const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, const CUtensorMap& tm_dz_st,
                      const BwdPArgs& a, int n_ctas, cudaStream_t s) {
   static bool configured = false;
+  bool& cooperative = g_mega_cooperative;   // the CTAs wait on one another: ask the driver to co-schedule the grid
   if (!configured) {
     cudaFuncSetAttribute(bwd_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmem);
     configured = true;
@@ -1189,11 +1193,23 @@ void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUt
   cfg.blockDim = dim3(kMegaThreads);
   cfg.dynamicSmemBytes = kMegaSmem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = a.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, bwd_mega_kernel, tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a);
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cooperative ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, bwd_mega_kernel, tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a);
+  if (e != cudaSuccess && cooperative) {
+    // cooperative + cluster launch not accepted by this driver: fall back to a plain launch (the grid is sized to
+    // the co-resident capacity reported by cudaOccupancyMaxActiveClusters, see capi.cu)
+    (void)cudaGetLastError();
+    cooperative = false;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, bwd_mega_kernel, tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a);
+  }
 }
+
 
 }  // namespace rnnt

@@ -7,7 +7,7 @@ from google.protobuf import text_format
 
 from myrtlespeech_b200.builders import speech_to_text as stt_builder
 from myrtlespeech_b200.protos import speech_to_text_pb2
-from myrtlespeech_b200.run.callbacks import RNNTTraining, ReportRNNTDecoder
+from myrtlespeech_b200.run.callbacks import BF16MixedPrecision, ClipGradNorm, RNNTTraining, ReportRNNTDecoder
 from myrtlespeech_b200.run.callbacks.rnn_t_training import _levenshtein
 
 
@@ -86,3 +86,47 @@ def test_one_training_step_and_eval_decode_under_the_loop_protocol():
     assert len(report.hypotheses) == B and all(isinstance(h, list) for h in report.hypotheses)
     rate = handler.state_dict["reports"]["RNNTGreedyDecoder/error_rate"]
     assert 0.0 <= rate
+
+
+def test_clip_grad_norm_clips_the_models_own_parameters():
+    lin = torch.nn.Linear(4, 4)
+    lin(torch.ones(2, 4)).sum().mul(100).backward()
+    clip = ClipGradNorm(lin, max_norm=1.0)
+    clip.on_backward_end()
+    total = torch.sqrt(sum((p.grad ** 2).sum() for p in lin.parameters()))
+    assert clip.last_norm > 1.0 and float(total) <= 1.0 + 1e-4
+    clip.on_batch_begin(last_input=None)  # other hooks are no-ops
+
+
+def test_checkpoint_keys_round_trip():
+    """Saver stores the container's state_dict (run/run.py:172-185); the joint's parameters are
+    ordinary ``fc.weight`` / ``fc.bias`` entries and reload with strict=True."""
+    torch.manual_seed(1)
+    a = stt_builder.build(text_format.Merge(CFG, speech_to_text_pb2.SpeechToText()))
+    b = stt_builder.build(text_format.Merge(CFG, speech_to_text_pb2.SpeechToText()))
+    sd = a.model.state_dict()
+    assert "joint.fc.weight" in sd and "joint.fc.bias" in sd
+    b.model.load_state_dict(sd, strict=True)
+    for (ka, va), (kb, vb) in zip(a.model.state_dict().items(), b.model.state_dict().items()):
+        assert ka == kb and torch.equal(va.cpu(), vb.cpu())
+
+
+@pytest.mark.gpu
+def test_bf16_autocast_training_step():
+    torch.manual_seed(0)
+    stt = stt_builder.build(text_format.Merge(CFG, speech_to_text_pb2.SpeechToText()))
+    handler = _Handler([BF16MixedPrecision(), RNNTTraining(), ClipGradNorm(stt, max_norm=5.0)])
+    B, T, U = 2, 9, 3
+    x = (torch.randn(B, T, 6), torch.tensor([9, 7]))
+    y = (torch.randint(0, 7, (B, U), dtype=torch.int32), torch.tensor([3, 2]))
+    xi, yi = handler.on_batch_begin(x, y)
+    assert xi[0][0].is_cuda
+    out, _ = stt.model(xi)
+    handler("on_loss_begin")
+    loss = stt.loss(out, yi)
+    loss.backward()
+    handler("on_backward_end")
+    assert torch.isfinite(loss) and float(loss) > 0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in stt.model.parameters())
+    assert handler.callbacks[2].last_norm is not None
+    handler("on_batch_end")
