@@ -253,6 +253,10 @@ long long rnnt_debug_get(const char* key) {
   }
   if (!strcmp(key, "n_classes")) return K_NCLASS;
   if (!strcmp(key, "mega_cooperative")) return bwd_mega_cooperative();
+  if (!strcmp(key, "max_ctas_fwd_c2")) return max_ctas_fwd_persist(2);
+  if (!strcmp(key, "max_ctas_fwd_c4")) return max_ctas_fwd_persist(4);
+  if (!strcmp(key, "max_ctas_mega_c2")) return max_ctas_bwd_mega(2);
+  if (!strcmp(key, "max_ctas_mega_c4")) return max_ctas_bwd_mega(4);
   return -1;
 }
 

@@ -45,6 +45,7 @@ constexpr int kMegaTmaWarp = 12, kMegaMmaWarp = 13;
 //   [3] MMA loop ns (%globaltimer)  [4] TMA waiting on hfull (hgen-starved)  [5] TMA waiting on empty
 //   [6] hgen busy cycles  [7] epilogue busy cycles (between tfull and tempty arrive)
 __device__ unsigned long long g_pprof[160 * 8];
+__device__ unsigned long long g_pprof2[160 * 8];   // second bank (RNNT_PROFILE builds): per-pass chunk issue cycles
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -70,6 +71,27 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int idx) {
 __device__ __forceinline__ void st_cg_u4(void* p, uint4 v) {
   asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
+}
+// Explicit shared-space accesses: through a generic pointer ptxas emits LD.E / ST.E (generic path, `lg` stalls in the
+// ncu source view) instead of LDS / STS.
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint16_t v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
 }
 // mbarrier / commit helpers on precomputed shared-window addresses (the issue loops keep running addresses
 // instead of re-deriving them from the stage index every k-block)
@@ -358,10 +380,10 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           tmem_ld_wait();
           const int c0 = j * p.nc + g * 32;
           float v[32];
-          const float4* bp = reinterpret_cast<const float4*>(sbias + c0);
+          const uint32_t bp = smem_u32(sbias + c0);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 bb = bp[q];
+            const float4 bb = lds128f(bp + 16 * q);
             v[4 * q + 0] = fmaf(__uint_as_float(raw[4 * q + 0]), kLog2e, bb.x);
             v[4 * q + 1] = fmaf(__uint_as_float(raw[4 * q + 1]), kLog2e, bb.y);
             v[4 * q + 2] = fmaf(__uint_as_float(raw[4 * q + 2]), kLog2e, bb.z);
@@ -467,9 +489,14 @@ __device__ __forceinline__ void wait_counter_ge(const unsigned* ptr, unsigned ta
     if (++spins > (1u << 26)) __trap();
   }
 }
-__device__ __forceinline__ uint4 ld_cg_u4(const void* ptr) {
+// h rows for the dh epilogue.  Each lane owns one lattice row, so a warp-wide 16-byte load touches 32 different
+// 128-byte lines; the eight loads that walk one row must be served by L1 (.ca) -- with .cg every one of them is a
+// separate L2 round trip and the dh epilogue takes 14.0k instead of 6.4k cycles per chunk (measured).  The rows
+// were written by this CTA's own hgen warps (same SM, ordered by the hfull mbarrier), so L1 cannot hold stale data
+// from another SM.
+__device__ __forceinline__ uint4 ld_ca_u4(const void* ptr) {
   uint4 v;
-  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  asm volatile("ld.global.ca.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
   return v;
 }
 __device__ __forceinline__ void tma_store_wait_all1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
@@ -625,6 +652,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         uint32_t ph = 0;
         bool ready = false;
         long long w_full = 0, w_tempty = 0;
+#ifdef RNNT_PROFILE
+        long long c_dz = 0, c_dh = 0, c_dz_max = 0, c_dh_max = 0, c_first = 0;
+#endif
         const long long c_begin = clock64();
         const unsigned long long ns_begin = gtimer_ns();
         for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P) {
@@ -636,6 +666,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
               const int buf = gc & 1;
               { PCNT_BEGIN(a); mbar_wait(&tempty_bar[buf], ((gc >> 1) & 1) ^ 1); PCNT_END(a, w_tempty); }
               const uint32_t d_tmem = tmem_base + buf * kNCmax;
+#ifdef RNNT_PROFILE
+              const long long chunk_t0 = clock64();
+#endif
               for (int k = 0; k < k_blocks; ++k) {
                 if (!ready) { PCNT_BEGIN(a); mbar_wait_a(fb, ph); PCNT_END(a, w_full); }
                 tc_fence_after();
@@ -653,6 +686,13 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 else { ad += kStageBytes >> 4; fb += 8; eb += 8; }
                 ready = mbar_try_wait_a(fb, ph);
               }
+#ifdef RNNT_PROFILE
+              {  // issue time of this chunk (tempty wait excluded): histogram by pass and slowness
+                const long long dtc = clock64() - chunk_t0;
+                if (pass == 0) { c_dz += dtc; if (dtc > c_dz_max) c_dz_max = dtc; } else { c_dh += dtc; if (dtc > c_dh_max) c_dh_max = dtc; }
+                if (j == 0) c_first += dtc;
+              }
+#endif
             }
           }
         }
@@ -661,6 +701,10 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           g_pprof[blockIdx.x * 8 + 1] = w_full;
           g_pprof[blockIdx.x * 8 + 2] = w_tempty;
           g_pprof[blockIdx.x * 8 + 3] = gtimer_ns() - ns_begin;
+#ifdef RNNT_PROFILE
+          g_pprof2[blockIdx.x * 8 + 0] = c_dz; g_pprof2[blockIdx.x * 8 + 1] = c_dh; g_pprof2[blockIdx.x * 8 + 2] = c_dz_max;
+          g_pprof2[blockIdx.x * 8 + 3] = c_dh_max; g_pprof2[blockIdx.x * 8 + 4] = c_first;
+#endif
         }
       }
     } else if (warp < 8) {
@@ -691,6 +735,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       n_my_sub = n_my_sub < 0 ? 0 : (n_my_sub > 2 ? 2 : n_my_sub);
 
       int gc = 0, it = 0;
+#ifdef RNNT_PROFILE
+      long long ep_hold_dz = 0, ep_tot_dz = 0, ep_hold_dh = 0, ep_tot_dh = 0;
+#endif
       for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P, ++it) {
         const int slot = it % p.NS, use = it / p.NS;
         const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
@@ -722,13 +769,16 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             const int buf = gc & 1;
             mbar_wait(&tfull_bar[buf], (gc >> 1) & 1);
             tc_fence_after();
+#ifdef RNNT_PROFILE
+            const long long ep_t0 = clock64();
+#endif
             for (int k = 0; k < n_my_box; ++k) {
               const int bcol = (2 * half + k) * 64;   // first column of the box inside the chunk
               uint8_t* sl = slice0 + k * 4096;
               // the previous TMA store out of this slice has finished reading it
               if (lane == 0) { if (n_my_box == 2) tma_store_wait_read1(); else tma_store_wait_read0(); }
               __syncwarp();
-              uint8_t* srow = sl + lane * 128;
+              const uint32_t srow = smem_u32(sl) + lane * 128;
 #pragma unroll
               for (int gg = 0; gg < 2; ++gg) {
                 const int cg = bcol + gg * 32;
@@ -736,11 +786,11 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                   uint32_t raw[32];
                   tmem_ld32(lane_taddr + buf * kNCmax + cg, raw);
                   tmem_ld_wait();
-                  const float4* bp = reinterpret_cast<const float4*>(sbias + j * p.nc_v + cg);
+                  const uint32_t bp = smem_u32(sbias + j * p.nc_v + cg);
                   uint32_t pk[16];
 #pragma unroll
                   for (int q = 0; q < 8; ++q) {
-                    const float4 bb = bp[q];
+                    const float4 bb = lds128f(bp + 16 * q);
                     const float d0 = ex2f(fmaf(__uint_as_float(raw[4 * q + 0]), kLog2e, bb.x) - lse2) * c0g;
                     const float d1 = ex2f(fmaf(__uint_as_float(raw[4 * q + 1]), kLog2e, bb.y) - lse2) * c0g;
                     const float d2 = ex2f(fmaf(__uint_as_float(raw[4 * q + 2]), kLog2e, bb.z) - lse2) * c0g;
@@ -750,24 +800,21 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                   }
 #pragma unroll
                   for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(srow + (((gg * 4 + q) ^ (lane & 7)) << 4)) =
-                        make_uint4(pk[4 * q + 0], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    sts128(srow + (((gg * 4 + q) ^ (lane & 7)) << 4), pk[4 * q + 0], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 } else {  // chunk ends inside this box: keep the pad columns defined (zero)
 #pragma unroll
                   for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(srow + (((gg * 4 + q) ^ (lane & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+                    sts128(srow + (((gg * 4 + q) ^ (lane & 7)) << 4), 0u, 0u, 0u, 0u);
                 }
               }
               // exact values for the two special columns of this row (avoids a bf16 read-modify-write)
               {
                 const int cb = p.blank - j * p.nc_v - bcol;
                 if (static_cast<unsigned>(cb) < 64u && p.blank - j * p.nc_v < p.nc_v)
-                  *reinterpret_cast<__nv_bfloat16*>(srow + (((cb >> 3) ^ (lane & 7)) << 4) + (cb & 7) * 2) =
-                      __float2bfloat16_rn(dv_blank);
+                  sts16(srow + (((cb >> 3) ^ (lane & 7)) << 4) + (cb & 7) * 2, __bfloat16_as_ushort(__float2bfloat16_rn(dv_blank)));
                 const int cl = label - j * p.nc_v - bcol;
                 if (label >= 0 && static_cast<unsigned>(cl) < 64u && label - j * p.nc_v < p.nc_v)
-                  *reinterpret_cast<__nv_bfloat16*>(srow + (((cl >> 3) ^ (lane & 7)) << 4) + (cl & 7) * 2) =
-                      __float2bfloat16_rn(dv_label);
+                  sts16(srow + (((cl >> 3) ^ (lane & 7)) << 4) + (cl & 7) * 2, __bfloat16_as_ushort(__float2bfloat16_rn(dv_label)));
               }
               fence_proxy_async_smem();
               __syncwarp();
@@ -780,17 +827,20 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_even_cta(&tempty_bar[buf]);
+#ifdef RNNT_PROFILE
+            ep_hold_dz += clock64() - ep_t0;
+#endif
             // db: column sums over this warp's 32 rows of each box (lane owns columns 2*lane, 2*lane + 1)
             if (!ghost && !(p.dbg & 32)) {
               for (int k = 0; k < n_my_box; ++k) {
                 const int bcol = (2 * half + k) * 64;
-                const uint8_t* colp = slice0 + k * 4096 + (lane & 3) * 4;
+                const uint32_t colp = smem_u32(slice0) + k * 4096 + (lane & 3) * 4;
                 const int ch = lane >> 2;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                 for (int rr = 0; rr < 32; rr += 2) {
-                  const uint32_t w0 = *reinterpret_cast<const uint32_t*>(colp + rr * 128 + ((ch ^ (rr & 7)) << 4));
-                  const uint32_t w1 = *reinterpret_cast<const uint32_t*>(colp + (rr + 1) * 128 + ((ch ^ ((rr + 1) & 7)) << 4));
+                  const uint32_t w0 = lds32(colp + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                  const uint32_t w1 = lds32(colp + (rr + 1) * 128 + ((ch ^ ((rr + 1) & 7)) << 4));
                   s0 += bf16lo(w0); s1 += bf16hi(w0);
                   s2 += bf16lo(w1); s3 += bf16hi(w1);
                 }
@@ -804,6 +854,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
               if (n_my_box == 2) tma_store_wait_all2(); else if (n_my_box == 1) tma_store_wait_all1();
               mbar_arrive(&dzr_bar[j - 1]);
             }
+#ifdef RNNT_PROFILE
+            ep_tot_dz += clock64() - ep_t0;
+#endif
           }
           if (lane == 0) {
             tma_store_wait_all0();
@@ -827,7 +880,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
               const uint4* hp = reinterpret_cast<const uint4*>(hrow + c0);
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                hv[gg * 4 + q] = (g * 32 < p.nc_h && c0 + 8 * q < p.H) ? ld_cg_u4(hp + q) : make_uint4(0, 0, 0, 0);
+                hv[gg * 4 + q] = (g * 32 < p.nc_h && c0 + 8 * q < p.H && !(p.dbg & 512)) ? ld_ca_u4(hp + q) : make_uint4(0, 0, 0, 0);
             }
           };
           uint4 hcur[8];
@@ -837,6 +890,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             const int buf = gc & 1;
             mbar_wait(&tfull_bar[buf], (gc >> 1) & 1);
             tc_fence_after();
+#ifdef RNNT_PROFILE
+            const long long eh_t0 = clock64();
+#endif
             if (n_my_sub == 0) {
               tc_fence_before();
               __syncwarp();
@@ -851,53 +907,58 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 #pragma unroll
                 for (int q = 0; q < 8; ++q) hnext[q] = make_uint4(0, 0, 0, 0);
               }
+              {
+                const uint32_t trow = smem_u32(tile_s) + (r * kDhPitch) * 4;
 #pragma unroll
-              for (int gg = 0; gg < 2; ++gg) {
-                const int g = sub * 2 + gg;
-                const int c0 = j * p.nc_h + g * 32;
-                float4* trow = reinterpret_cast<float4*>(tile_s + r * kDhPitch + gg * 32);
-                if (g * 32 < p.nc_h && c0 < p.H && !(p.dbg & 128)) {
-                  uint32_t raw[32];
-                  tmem_ld32(lane_taddr + buf * kNCmax + g * 32, raw);
-                  tmem_ld_wait();
+                for (int gg = 0; gg < 2; ++gg) {
+                  const int g = sub * 2 + gg;
+                  const int c0 = j * p.nc_h + g * 32;
+                  if (g * 32 < p.nc_h && c0 < p.H && !(p.dbg & 128)) {
+                    uint32_t raw[32];
+                    tmem_ld32(lane_taddr + buf * kNCmax + g * 32, raw);
+                    tmem_ld_wait();
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const uint4 hq = hcur[gg * 4 + q];
-                    const uint32_t w[4] = {hq.x, hq.y, hq.z, hq.w};
-                    float o[8];
+                    for (int q = 0; q < 4; ++q) {
+                      const uint4 hq = hcur[gg * 4 + q];
+                      const uint32_t w[4] = {hq.x, hq.y, hq.z, hq.w};
+                      float o[8];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float h0 = bf16lo(w[e]), h1 = bf16hi(w[e]);
-                      const float d0 = __uint_as_float(raw[8 * q + 2 * e]);
-                      const float d1 = __uint_as_float(raw[8 * q + 2 * e + 1]);
-                      o[2 * e] = fmaf(-h0 * h0, d0, d0);
-                      o[2 * e + 1] = fmaf(-h1 * h1, d1, d1);
+                      for (int e = 0; e < 4; ++e) {
+                        const float h0 = bf16lo(w[e]), h1 = bf16hi(w[e]);
+                        const float d0 = __uint_as_float(raw[8 * q + 2 * e]);
+                        const float d1 = __uint_as_float(raw[8 * q + 2 * e + 1]);
+                        o[2 * e] = fmaf(-h0 * h0, d0, d0);
+                        o[2 * e + 1] = fmaf(-h1 * h1, d1, d1);
+                      }
+                      sts128f(trow + (gg * 32 + 8 * q) * 4, o[0], o[1], o[2], o[3]);
+                      sts128f(trow + (gg * 32 + 8 * q + 4) * 4, o[4], o[5], o[6], o[7]);
                     }
-                    trow[2 * q] = make_float4(o[0], o[1], o[2], o[3]);
-                    trow[2 * q + 1] = make_float4(o[4], o[5], o[6], o[7]);
-                  }
-                } else if (!(p.dbg & 128)) {
+                  } else if (!(p.dbg & 128)) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) trow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < 8; ++i) sts128f(trow + (gg * 32 + 4 * i) * 4, 0.f, 0.f, 0.f, 0.f);
+                  }
                 }
               }
               if (q2 == n_my_sub - 1) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_even_cta(&tempty_bar[buf]);
+#ifdef RNNT_PROFILE
+                ep_hold_dh += clock64() - eh_t0;
+#endif
               }
               named_bar_sync(set_bar, kEpiThreads);  // the set's dpre tile (128 rows x 64 columns) is complete
               const int c4 = et & 15;
               const int colbase = j * p.nc_h + sub * 64 + 4 * c4;
               if (!ghost && !(p.dbg & 64) && sub * 64 + 4 * c4 < p.nc_h && colbase < p.H) {
-                const float* tcol = tile_s + 4 * c4;
+                const uint32_t tcol = smem_u32(tile_s) + 16 * c4;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {  // df: sum over the 8 label positions of frame a
                   const int a = (et >> 4) + 8 * k;
                   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                   for (int c = 0; c < kTU; ++c) {
-                    const float4 v = *reinterpret_cast<const float4*>(tcol + (a * kTU + c) * kDhPitch);
+                    const float4 v = lds128f(tcol + (a * kTU + c) * (kDhPitch * 4));
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                   }
                   if (ti.t0 + a < ti.T)
@@ -909,7 +970,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                   for (int a = 0; a < kTT; ++a) {
-                    const float4 v = *reinterpret_cast<const float4*>(tcol + (a * kTU + c) * kDhPitch);
+                    const float4 v = lds128f(tcol + (a * kTU + c) * (kDhPitch * 4));
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                   }
                   if (ti.u0 + c <= ti.U)
@@ -921,11 +982,21 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 #pragma unroll
               for (int q = 0; q < 8; ++q) hcur[q] = hnext[q];
             }
+#ifdef RNNT_PROFILE
+            ep_tot_dh += clock64() - eh_t0;
+#endif
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&hfree_bar[slot]);
         }
       }
+#ifdef RNNT_PROFILE
+      if ((p.dbg & 4) && lane == 0 && (warp == 0 || warp == 4)) {
+        const int o = blockIdx.x * 8 + (warp == 0 ? 5 : 6);   // bank 2: [5] set 0, [6] set 1: packed hold/total means
+        g_pprof2[o] = (static_cast<unsigned long long>(ep_hold_dz >> 10) << 48) | (static_cast<unsigned long long>(ep_tot_dz >> 10) << 32) |
+                      (static_cast<unsigned long long>(ep_hold_dh >> 10) << 16) | static_cast<unsigned long long>(ep_tot_dh >> 10);
+      }
+#endif
     } else if (warp >= 10) {
       // ------------------------------- hgen (warps 10, 11, 14, 15) --------------------
       const int ht = ((warp & 1) + ((warp >> 2) & 1) * 2) * 32 + lane;   // 10->0, 11->1, 14->2, 15->3
@@ -1130,8 +1201,11 @@ int max_ctas_fwd_persist(int csize) {
   return cached[csize];
 }
 int read_persist_prof(unsigned long long* out, int n) {
-  if (n > 160 * 8) n = 160 * 8;
-  return cudaMemcpyFromSymbol(out, g_pprof, sizeof(unsigned long long) * n) == cudaSuccess ? n : -1;
+  if (n > 2 * 160 * 8) n = 2 * 160 * 8;
+  const int n1 = n > 160 * 8 ? 160 * 8 : n;
+  if (cudaMemcpyFromSymbol(out, g_pprof, sizeof(unsigned long long) * n1) != cudaSuccess) return -1;
+  if (n > n1 && cudaMemcpyFromSymbol(out + n1, g_pprof2, sizeof(unsigned long long) * (n - n1)) != cudaSuccess) return -1;
+  return n;
 }
 
 void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
