@@ -239,6 +239,7 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "time_kernels")) g_time_kernels = value != 0;
   if (!strcmp(key, "gemm_dbg")) set_gemm_dbg(value);
   if (!strcmp(key, "path")) g_path = value;
+  if (!strcmp(key, "mega_cooperative")) set_bwd_mega_cooperative(value);  // 0: plain launch (ncu cannot replay cooperative launches)
   if (!strcmp(key, "cluster") && (value == 2 || value == 4)) g_cluster = value;
   if (!strcmp(key, "cluster_bwd") && (value == 2 || value == 4)) g_cluster_bwd = value;
   if (!strcmp(key, "ring_slots") && value >= 2 && value <= 4) g_ring_slots = value;

@@ -148,6 +148,7 @@ void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUt
 int smem_bytes_bwd_mega();
 int max_ctas_bwd_mega(int csize);
 int bwd_mega_cooperative();   // 1 while the cooperative (co-scheduled) launch is in use
+void set_bwd_mega_cooperative(int v);
 
 void set_gemm_dbg(int v);
 int read_gemm_prof(unsigned long long* out, int n);

@@ -1252,6 +1252,7 @@ int max_ctas_bwd_mega(int csize) {
 
 static bool g_mega_cooperative = true;
 int bwd_mega_cooperative() { return g_mega_cooperative ? 1 : 0; }
+void set_bwd_mega_cooperative(int v) { g_mega_cooperative = v != 0; }
 
 void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUtensorMap& tm_dz, const CUtensorMap& tm_wt,
                      const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, const CUtensorMap& tm_dz_st,
