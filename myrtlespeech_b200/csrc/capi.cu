@@ -381,10 +381,18 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
 
   const int nc_v = chunk_cols(V), nc_h = chunk_cols(H);
   if (g_path == 1 && p.mega_ok && max_ctas_bwd_mega(2) >= 2 * (p.P + p.C)) {
-    const uint64_t ring_rows = static_cast<uint64_t>(p.P) * p.NS * 2 * kTileRows;
-    // 4-clusters need both roles to start on a cluster boundary and both W chunk widths to split into quarters
-    const int csize = (g_cluster_bwd == 4 && p.P % 2 == 0 && p.C % 2 == 0 && nc_v % 32 == 0 && nc_h % 32 == 0 &&
-                       max_ctas_bwd_mega(4) >= 2 * (p.P + p.C)) ? 4 : 2;
+    // 4-clusters (operand multicast between two pairs of one role): both roles must start on a cluster boundary,
+    // both W chunk widths must split into quarters, and only the co-resident capacity for 4-clusters (132 of 148
+    // CTAs on this part) can be used, so the producers give up the difference.
+    int P = p.P;
+    int csize = 2;
+    if (g_cluster_bwd == 4 && p.C % 2 == 0 && nc_v % 32 == 0 && nc_h % 32 == 0) {
+      int P4 = max_ctas_bwd_mega(4) / 2 - p.C;
+      if (P4 > p.P) P4 = p.P;
+      P4 &= ~1;
+      if (P4 >= 2) { P = P4; csize = 4; }
+    }
+    const uint64_t ring_rows = static_cast<uint64_t>(P) * p.NS * 2 * kTileRows;
     const int wdiv = csize == 4 ? 4 : 2;
     CUtensorMap tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st;
     if ((rc = make_map(&tm_dz_st, w.at<void>(p.o_dzring), p.Vp, ring_rows, p.Vp, 64, 32))) return rc;
@@ -402,14 +410,14 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
     a.nc_v = nc_v; a.n_chunks_v = (V + nc_v - 1) / nc_v; a.kb_h = (H + 63) / 64;
     a.nc_h = nc_h; a.n_chunks_h = (H + nc_h - 1) / nc_h; a.kb_v = p.Vp / 64;
     a.blank = blank; a.Umax = d.Umax;
-    a.P = p.P; a.C = p.C; a.KG = p.KG; a.NS = p.NS; a.n_vt = p.n_vt; a.n_ht = p.n_ht; a.n_out = p.n_out;
+    a.P = P; a.C = p.C; a.KG = p.KG; a.NS = p.NS; a.n_vt = p.n_vt; a.n_ht = p.n_ht; a.n_out = p.n_out;
     a.f = static_cast<const __nv_bfloat16*>(f); a.g = static_cast<const __nv_bfloat16*>(g);
     a.h_ring = w.at<__nv_bfloat16>(p.o_hring);
     a.bias = bias; a.y = y; a.lse_tile = w.at<float>(p.o_lse); a.lpb = w.at<float>(p.o_lpb); a.lpl = w.at<float>(p.o_lpl);
     a.c1 = w.at<float>(p.o_c1); a.c2 = w.at<float>(p.o_c2); a.grad_loss = grad_loss;
     a.db = db; a.df = df; a.dg = dg; a.dW = dW;
     a.ready = w.at<unsigned>(p.o_flags); a.done = w.at<unsigned>(p.o_flags) + n_flags;
-    KLAUNCH(K_BWD_MEGA, s, launch_bwd_mega(tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a, 2 * (p.P + p.C), s));
+    KLAUNCH(K_BWD_MEGA, s, launch_bwd_mega(tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a, 2 * (P + p.C), s));
     CUDA_TRY(cudaGetLastError());
     return RNNT_OK;
   }
