@@ -191,6 +191,49 @@ __device__ __forceinline__ void hgen_tile(const TileInfo& ti, const __nv_bfloat1
   }
 }
 
+
+// ---- MMA issue of one accumulator chunk (all k-blocks) ---------------------------------------------------
+// Running state of the TMA->MMA stage ring as seen by the issuing warp.
+struct RingState {
+  int s;            // stage index
+  uint32_t ph;      // phase parity of the current ring round
+  uint64_t ad;      // smem descriptor of the current stage's A tile (B = A + 16 KB)
+  uint32_t fb, eb;  // shared-window addresses of the current stage's full / empty barriers
+  bool ready;       // the current stage's full barrier was already seen complete (poll ahead)
+};
+
+// Issues the MMAs of `k_blocks` k-blocks into `d_tmem` and commits: every stage's empty barrier (`all_mask`), the
+// chunk's `tfull` barrier and, if non-zero, `extra` after the last k-block (`pair_mask`).  (Handling two stages per
+// loop iteration was tried and is slower: waiting for the second stage before issuing the first one's MMAs
+// exposes the TMA feed, 10.2k -> 11.9k cycles per chunk.)
+template <int kStages>
+__device__ __forceinline__ void issue_chunk(RingState& st, const uint64_t ad0, const uint32_t fb0, const uint32_t eb0,
+                                            const uint32_t d_tmem, const uint32_t idesc, const int k_blocks,
+                                            const uint16_t all_mask, const uint16_t pair_mask, const uint32_t tfull,
+                                            const uint32_t extra) {
+  constexpr uint32_t kStep = kStageBytes >> 4;
+  int k = 0;
+  for (; k < k_blocks; ++k) {
+    if (!st.ready) mbar_wait_a(st.fb, st.ph);
+    tc_fence_after();
+    const uint64_t a0 = st.ad, b0 = a0 + (kAStage >> 4);
+    const bool last = k + 1 == k_blocks;
+    if (elect_one()) {
+#pragma unroll
+      for (int kk = 0; kk < kBK / 16; ++kk) umma_bf16_pair(d_tmem, a0 + 2 * kk, b0 + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+      umma_commit_pair_a(st.eb, all_mask);
+      if (last) {
+        umma_commit_pair_a(tfull, pair_mask);
+        if (extra) umma_commit_pair_a(extra, pair_mask);
+      }
+    }
+    __syncwarp();
+    if (++st.s == kStages) { st.s = 0; st.ph ^= 1; st.ad = ad0; st.fb = fb0; st.eb = eb0; }
+    else { st.ad += kStep; st.fb += 8; st.eb += 8; }
+    st.ready = mbar_try_wait_a(st.fb, st.ph);
+  }
+}
+
 constexpr int kFwdStages = 6;
 constexpr int kFwdSmem = kFwdStages * kStageBytes + kMaxBiasCols * 4 + 1024 + 256;
 
@@ -302,11 +345,8 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       // running stage state: descriptor of the stage's A tile (B = A + 16 KB), full / empty barrier addresses
       const uint64_t ad0 = make_smem_desc_sw128(smem_u32(stage_base), 16, 1024);
       const uint32_t fb0 = smem_u32(&full_bar[0]), eb0 = smem_u32(&empty_bar[0]);
-      uint64_t ad = ad0;
-      uint32_t fb = fb0, eb = eb0;
-      int s = 0, gc = 0, it = 0;
-      uint32_t ph = 0;
-      bool ready = false;
+      RingState st{0, 0u, ad0, fb0, eb0, false};
+      int gc = 0, it = 0;
       long long w_full = 0, w_tempty = 0;
       const long long c_begin = clock64();
       const unsigned long long ns_begin = gtimer_ns();
@@ -314,30 +354,12 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         for (int j = 0; j < p.n_chunks; ++j, ++gc) {
           const int buf = gc & 1;
           { PCNT_BEGIN(a); mbar_wait(&tempty_bar[buf], ((gc >> 1) & 1) ^ 1); PCNT_END(a, w_tempty); }
-          const uint32_t d_tmem = tmem_base + buf * kNCmax;
-          const bool last_chunk = j == p.n_chunks - 1;
-          for (int k = 0; k < p.k_blocks; ++k) {
-            if (!ready) { PCNT_BEGIN(a); mbar_wait_a(fb, ph); PCNT_END(a, w_full); }
-            tc_fence_after();
-            const uint64_t bd = ad + (kAStage >> 4);
-            const bool last_k = k == p.k_blocks - 1;
-            if (elect_one()) {
-#pragma unroll
-              for (int kk = 0; kk < kBK / 16; ++kk)
-                umma_bf16_pair(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-              umma_commit_pair_a(eb, all_mask);   // the stage is free once BOTH pairs have consumed it
-              if (last_k) {
-                umma_commit_pair(&tfull_bar[buf], pair_mask);
-                if (last_chunk) umma_commit_pair(&hempty_bar[it & 1], pair_mask);  // scratch tile fully consumed
-              }
-            }
-            __syncwarp();
-            if (++s == kStages) { s = 0; ph ^= 1; ad = ad0; fb = fb0; eb = eb0; }
-            else { ad += kStageBytes >> 4; fb += 8; eb += 8; }
-            ready = mbar_try_wait_a(fb, ph);  // poll ahead: the next wait is off the critical path
-          }
+          issue_chunk<kStages>(st, ad0, fb0, eb0, tmem_base + buf * kNCmax, idesc, p.k_blocks, all_mask, pair_mask,
+                               smem_u32(&tfull_bar[buf]),
+                               j == p.n_chunks - 1 ? smem_u32(&hempty_bar[it & 1]) : 0u);  // scratch tile consumed
         }
       }
+      (void)w_full;
       if ((p.dbg & 4) && lane == 0) {
         g_pprof[blockIdx.x * 8 + 0] = clock64() - c_begin;
         g_pprof[blockIdx.x * 8 + 1] = w_full;
@@ -646,11 +668,8 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         const uint32_t idesc_h = make_idesc_bf16(2 * kBM, p.nc_h, false, false);
         const uint64_t ad0 = make_smem_desc_sw128(smem_u32(stage_base), 16, 1024);
         const uint32_t fb0 = smem_u32(&full_bar[0]), eb0 = smem_u32(&empty_bar[0]);
-        uint64_t ad = ad0;
-        uint32_t fb = fb0, eb = eb0;
-        int s = 0, gc = 0;
-        uint32_t ph = 0;
-        bool ready = false;
+        RingState st{0, 0u, ad0, fb0, eb0, false};
+        int gc = 0;
         long long w_full = 0, w_tempty = 0;
 #ifdef RNNT_PROFILE
         long long c_dz = 0, c_dh = 0, c_dz_max = 0, c_dh_max = 0, c_first = 0;
@@ -665,27 +684,11 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             for (int j = 0; j < n_chunks; ++j, ++gc) {
               const int buf = gc & 1;
               { PCNT_BEGIN(a); mbar_wait(&tempty_bar[buf], ((gc >> 1) & 1) ^ 1); PCNT_END(a, w_tempty); }
-              const uint32_t d_tmem = tmem_base + buf * kNCmax;
 #ifdef RNNT_PROFILE
               const long long chunk_t0 = clock64();
 #endif
-              for (int k = 0; k < k_blocks; ++k) {
-                if (!ready) { PCNT_BEGIN(a); mbar_wait_a(fb, ph); PCNT_END(a, w_full); }
-                tc_fence_after();
-                const uint64_t bd = ad + (kAStage >> 4);
-                const bool last_k = k == k_blocks - 1;
-                if (elect_one()) {
-#pragma unroll
-                  for (int kk = 0; kk < kBK / 16; ++kk)
-                    umma_bf16_pair(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-                  umma_commit_pair_a(eb, all_mask);
-                  if (last_k) umma_commit_pair(&tfull_bar[buf], pair_mask);
-                }
-                __syncwarp();
-                if (++s == kStages) { s = 0; ph ^= 1; ad = ad0; fb = fb0; eb = eb0; }
-                else { ad += kStageBytes >> 4; fb += 8; eb += 8; }
-                ready = mbar_try_wait_a(fb, ph);
-              }
+              issue_chunk<kStages>(st, ad0, fb0, eb0, tmem_base + buf * kNCmax, idesc, k_blocks, all_mask, pair_mask,
+                                   smem_u32(&tfull_bar[buf]), 0u);
 #ifdef RNNT_PROFILE
               {  // issue time of this chunk (tempty wait excluded): histogram by pass and slowness
                 const long long dtc = clock64() - chunk_t0;
@@ -696,6 +699,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             }
           }
         }
+        (void)w_full;
         if ((p.dbg & 4) && lane == 0) {
           g_pprof[blockIdx.x * 8 + 0] = clock64() - c_begin;
           g_pprof[blockIdx.x * 8 + 1] = w_full;

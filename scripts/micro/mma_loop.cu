@@ -165,6 +165,22 @@ __global__ void __launch_bounds__(192, 1) mma_loop_kernel(const __grid_constant_
     // shared-memory traffic generator in the 6 KB x 4 warps after the stage ring (no TMEM access)
     uint4* region = reinterpret_cast<uint4*>(smem + 6 * 32768) + (warp - 2) * 256;   // 4 KB per warp
     uint4 acc = make_uint4(0, 0, 0, 0);
+    long long n_bytes = 0;
+    if (c.lsu >= 3) {
+      // high-bandwidth variant: 16 independent LDS.128 (lsu=3) or 8 STS.128 + 8 LDS.128 (lsu=4) per iteration
+      while (!stop_flag) {
+        uint4 v[16];
+        if (c.lsu == 4) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) region[i * 32 + lane] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = region[(i & 7) * 32 + ((lane + i) & 31)];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { acc.x ^= v[i].x; acc.y += v[i].y; }
+        n_bytes += 16 * 512 + (c.lsu == 4 ? 8 * 512 : 0);
+      }
+    } else
     while (!stop_flag) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -172,7 +188,9 @@ __global__ void __launch_bounds__(192, 1) mma_loop_kernel(const __grid_constant_
         const uint4 v = region[((i + 1) & 7) * 32 + lane];
         acc.x ^= v.x; acc.y += v.y; acc.z ^= v.z; acc.w += v.w;
       }
+      n_bytes += 8 * 512 * (c.lsu == 2 ? 2 : 1);
     }
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&out_cycles[150 + (blockIdx.x & 1)]), static_cast<unsigned long long>(n_bytes));
     if (acc.x == 0x12345678u) out_cycles[146] = acc.y;
   } else if (c.epi % 10) {
     // epilogue-like TMEM readers on buffer 1 (values irrelevant)
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(192, 1) mma_loop_kernel(const __grid_constant_
 }
 
 int main(int argc, char** argv) {
-  long long* d_out; cudaMalloc(&d_out, sizeof(long long) * 148);
+  long long* d_out; cudaMalloc(&d_out, sizeof(long long) * 160);
   const int smem = 216 * 1024;
   PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
   { void* pp = nullptr; cudaDriverEntryPointQueryResult q;
@@ -208,12 +226,11 @@ int main(int argc, char** argv) {
   cudaFuncSetAttribute(mma_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   Cfg cfgs[] = {
     //  n_kb st full fence mask lanes chunk epi lean tma lsu
-    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 0, 0},
     {20000, 6, 1, 1, 3, 1, 16, 10, 3, 1, 0},
-    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 1, 1},
     {20000, 6, 1, 1, 3, 1, 16, 10, 3, 1, 2},
-    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 0, 2},
-    {20000, 4, 1, 1, 3, 1, 16, 10, 3, 1, 0},
+    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 1, 3},
+    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 1, 4},
+    {20000, 6, 1, 1, 3, 1, 16, 10, 3, 0, 3},
   };
   for (auto& c : cfgs) {
     for (int grid : {148}) {
@@ -221,7 +238,7 @@ int main(int argc, char** argv) {
       cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       lc.attrs = at; lc.numAttrs = 1;
-      cudaMemset(d_out, 0, sizeof(long long) * 148);
+      cudaMemset(d_out, 0, sizeof(long long) * 160);
       for (int rep = 0; rep < 2; ++rep) {
         cudaError_t le = cudaLaunchKernelEx(&lc, mma_loop_kernel, tm, c, d_out);
         if (le != cudaSuccess) printf("launch error %s\n", cudaGetErrorString(le));
@@ -235,6 +252,8 @@ int main(int argc, char** argv) {
       long long mx = 0; for (int i = 0; i < grid; i += 2) if (h[i] > mx) mx = h[i];
       printf("grid=%3d stages=%d tma=%d lsu=%d chunk=%2d epi=%d lean=%d : %7.1f cyc/k-block (%5.1f per MMA)\n", grid,
              c.stages, c.tma, c.lsu, c.chunk_kb, c.epi, c.lean, (double)mx / c.n_kb, (double)mx / c.n_kb / 4);
+      { long long hb[2]; cudaMemcpy(hb, d_out + 150, sizeof(hb), cudaMemcpyDeviceToHost);
+        printf("    LSU shared-memory traffic per CTA: %.1f B/clk (4 warps)\n", grid > 2 ? (double)(hb[0] + hb[1]) / 148.0 / (double)mx : (double)hb[0] / (double)mx); }
       printf("    kernel %.3f ms -> %.1f ns per MMA, %.1f TFLOP/s chip, effective clock %.3f GHz\n", ms, ms * 1e6 / (c.n_kb * 4.0), 74.0 * c.n_kb * 4.0 * 2 * 256 * 256 * 16 / (ms * 1e-3) / 1e12, mx / (ms * 1e6));
       fflush(stdout);
     }
