@@ -140,7 +140,9 @@ __device__ __forceinline__ void tma_load_2d_pair_mcast(uint32_t smem_dst, const 
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // h rows of one tile -> dst[128][H] (row = dt * 8 + du); rows outside the utterance's lattice are zero.
-// Called by the 128 hgen threads (ht = 0..127); each owns 8-column vectors cv = ht, ht + 128, ...
+// Called by the 128 hgen threads (ht = 0..127).  A thread owns one 8-column vector and a range of frames: with
+// H >= 1024 every thread walks all 16 frames of its vectors cv = ht, ht + 128, ...; with fewer vectors than threads
+// (H < 1024) the frames are split between thread groups so that all four warps (one per MUFU unit) stay busy.
 __device__ __forceinline__ void hgen_tile(const TileInfo& ti, const __nv_bfloat16* __restrict__ f,
                                           const __nv_bfloat16* __restrict__ g, __nv_bfloat16* dst, int H, int Tmax,
                                           int U1max, int ht) {
@@ -148,7 +150,18 @@ __device__ __forceinline__ void hgen_tile(const TileInfo& ti, const __nv_bfloat1
   int nt = ti.T - ti.t0; nt = nt < 0 ? 0 : (nt > kTT ? kTT : nt);
   int nu = ti.U + 1 - ti.u0; nu = nu < 0 ? 0 : (nu > kTU ? kTU : nu);
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  for (int cv = ht; cv < nvec; cv += kHgenThreads) {
+  int cv0 = ht, cv_step = kHgenThreads, dt0 = 0, dt1 = kTT;
+  if (nvec < kHgenThreads) {
+    const int n_groups = kHgenThreads / nvec;                 // >= 1
+    const int fpg = (kTT + n_groups - 1) / n_groups;          // frames per group
+    const int grp = ht / nvec;
+    cv0 = ht - grp * nvec;
+    cv_step = nvec;                                           // one vector per thread
+    dt0 = grp * fpg;
+    dt1 = dt0 + fpg < kTT ? dt0 + fpg : kTT;
+    if (grp >= n_groups || dt0 >= kTT) return;
+  }
+  for (int cv = cv0; cv < nvec; cv += cv_step) {
     float gv[kTU][8];
 #pragma unroll
     for (int du = 0; du < kTU; ++du) {
@@ -159,11 +172,11 @@ __device__ __forceinline__ void hgen_tile(const TileInfo& ti, const __nv_bfloat1
       for (int e = 0; e < 4; ++e) { gv[du][2 * e] = bf16lo(w[e]); gv[du][2 * e + 1] = bf16hi(w[e]); }
     }
     uint4 fq = zero;
-    if (nt > 0) fq = __ldg(reinterpret_cast<const uint4*>(f + (static_cast<size_t>(ti.b) * Tmax + ti.t0) * H) + cv);
+    if (dt0 < nt) fq = __ldg(reinterpret_cast<const uint4*>(f + (static_cast<size_t>(ti.b) * Tmax + ti.t0 + dt0) * H) + cv);
 #pragma unroll 1
-    for (int dt = 0; dt < kTT; ++dt) {
+    for (int dt = dt0; dt < dt1; ++dt) {
       uint4 fnext = zero;
-      if (dt + 1 < nt)
+      if (dt + 1 < nt && dt + 1 < dt1)
         fnext = __ldg(reinterpret_cast<const uint4*>(f + (static_cast<size_t>(ti.b) * Tmax + ti.t0 + dt + 1) * H) + cv);
       __nv_bfloat16* orow = dst + static_cast<size_t>(dt * kTU) * H + cv * 8;
       if (dt < nt) {
@@ -190,7 +203,6 @@ __device__ __forceinline__ void hgen_tile(const TileInfo& ti, const __nv_bfloat1
     }
   }
 }
-
 
 // ---- MMA issue of one accumulator chunk (all k-blocks) ---------------------------------------------------
 // Running state of the TMA->MMA stage ring as seen by the issuing warp.
