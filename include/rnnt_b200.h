@@ -85,6 +85,18 @@ int rnnt_lattice_forward(const float* lp_blank, const float* lp_label, const int
 int rnnt_greedy_joint_argmax(const void* f, const void* g, const void* W, const float* bias,
                              const int32_t* t_idx, int32_t* out_k, int B, int Tmax, int V, int H, void* stream);
 
+/* One whole greedy decode step for B utterances, bookkeeping included (the loop body of
+ * src/myrtlespeech/post_process/ctc_greedy_decoder.py:77-92 without its per-frame host sync).  For every utterance with
+ * t_cur[b] < lens[b]: k = argmax_v (W . tanh(f[b][t_cur[b]] + bf16(g[b])) + bias); if k != blank it is appended to
+ * sym[b][n_sym[b]++] and emitted[b] is incremented; the frame advances (t_cur[b]++, emitted[b] = 0) on blank or once
+ * max_symbols were emitted at this frame.  is_sym[b] / label[b] tell the caller where to step the prediction network
+ * (label = 0 where nothing was emitted); active[b] = t_cur[b] < lens[b] after the update.  g is f32 [B][H]; all state
+ * arrays are DEVICE int32 and updated in place. */
+int rnnt_greedy_step(const void* f, const float* g, const void* W, const float* bias, const int32_t* lens,
+                     int32_t* t_cur, int32_t* emitted, int32_t* n_sym, int32_t* sym, int sym_cap, int32_t* is_sym,
+                     int32_t* label, int32_t* active, int B, int Tmax, int V, int H, int blank, int max_symbols,
+                     void* stream);
+
 /* Debug / test hooks (not part of the drop-in surface). */
 int rnnt_debug_copy_stats(const void* workspace, int B, int Tmax, int Umax, int V, int H, float* lp_blank,
                           float* lp_label, float* c_blank, float* c_label, float* lnp_beta, void* stream);

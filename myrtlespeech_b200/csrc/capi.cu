@@ -506,6 +506,24 @@ int rnnt_greedy_joint_argmax(const void* f, const void* g, const void* W, const 
   return RNNT_OK;
 }
 
+int rnnt_greedy_step(const void* f, const float* g, const void* W, const float* bias, const int32_t* lens,
+                     int32_t* t_cur, int32_t* emitted, int32_t* n_sym, int32_t* sym, int sym_cap, int32_t* is_sym,
+                     int32_t* label, int32_t* active, int B, int Tmax, int V, int H, int blank, int max_symbols,
+                     void* stream) {
+  if (B < 1 || Tmax < 1 || V < 1 || sym_cap < 1 || max_symbols < 1)
+    return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d V=%d sym_cap=%d max_symbols=%d out of range", B, Tmax, V, sym_cap, max_symbols);
+  if (H < 8 || H % 8 != 0 || H > 8192) return fail(RNNT_ERR_UNSUPPORTED, "H=%d must be a multiple of 8 in [8, 8192]", H);
+  if (blank < 0 || blank >= V) return fail(RNNT_ERR_INVALID_ARGUMENT, "blank=%d must be in [0, %d]", blank, V - 1);
+  if (!f || !g || !W || !lens || !t_cur || !emitted || !n_sym || !sym || !is_sym || !label || !active)
+    return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+  KLAUNCH(K_MISC, static_cast<cudaStream_t>(stream),
+          launch_greedy_step(static_cast<const __nv_bfloat16*>(f), g, static_cast<const __nv_bfloat16*>(W), bias, lens, t_cur,
+                             emitted, n_sym, sym, sym_cap, is_sym, label, active, B, Tmax, V, H, blank, max_symbols,
+                             static_cast<cudaStream_t>(stream)));
+  CUDA_TRY(cudaGetLastError());
+  return RNNT_OK;
+}
+
 int rnnt_debug_copy_stats(const void* workspace, int B, int Tmax, int Umax, int V, int H, float* lp_blank,
                           float* lp_label, float* c_blank, float* c_label, float* lnp_beta, void* stream) {
   int rc = check_dims(B, Tmax, Umax, V, H);

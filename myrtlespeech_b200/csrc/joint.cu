@@ -745,6 +745,74 @@ greedy_argmax_kernel(const __nv_bfloat16* __restrict__ f, const __nv_bfloat16* _
   }
 }
 
+// One greedy decode step with the bookkeeping fused in: for every utterance still inside its frames, the joint argmax at
+// its current frame, then (one thread) emit / count / advance exactly as the reference-style host loop did.
+// State arrays are device int32 and updated in place.
+__global__ void __launch_bounds__(256)
+greedy_step_kernel(const __nv_bfloat16* __restrict__ f, const float* __restrict__ g, const __nv_bfloat16* __restrict__ W,
+                   const float* __restrict__ bias, const int* __restrict__ lens, int* __restrict__ t_cur,
+                   int* __restrict__ emitted, int* __restrict__ n_sym, int* __restrict__ sym, int sym_cap,
+                   int* __restrict__ is_sym, int* __restrict__ label, int* __restrict__ active, int Tmax, int V, int H,
+                   int blank, int max_symbols) {
+  extern __shared__ float sh[];  // H floats of h, then per-warp (value, index) pairs
+  const int b = blockIdx.x;
+  const int t = t_cur[b];
+  if (t >= lens[b]) {            // finished utterance: nothing changes
+    if (threadIdx.x == 0) { is_sym[b] = 0; label[b] = 0; active[b] = 0; }
+    return;
+  }
+  const __nv_bfloat16* fr = f + (static_cast<size_t>(b) * Tmax + t) * H;
+  const float* gr = g + static_cast<size_t>(b) * H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const float x = __bfloat162float(fr[i]) + __bfloat162float(__float2bfloat16_rn(gr[i]));
+    sh[i] = __bfloat162float(__float2bfloat16_rn(tanh_approx(x)));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  float best = -INFINITY;
+  int best_k = 0x7fffffff;
+  for (int v = warp; v < V; v += nwarp) {
+    const __nv_bfloat16* wr = W + static_cast<size_t>(v) * H;
+    float acc = 0.0f;
+    for (int i = lane * 8; i < H; i += 256) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(wr + i));
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc = fmaf(bf16lo(ww[e]), sh[i + 2 * e], acc);
+        acc = fmaf(bf16hi(ww[e]), sh[i + 2 * e + 1], acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    acc += bias ? bias[v] : 0.0f;
+    if (acc > best || (acc == best && v < best_k)) { best = acc; best_k = v; }
+  }
+  float* rv = sh + H;
+  int* ri = reinterpret_cast<int*>(rv + nwarp);
+  if (lane == 0) { rv[warp] = best; ri[warp] = best_k; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nwarp; ++w)
+      if (rv[w] > best || (rv[w] == best && ri[w] < best_k)) { best = rv[w]; best_k = ri[w]; }
+    const bool is = best_k != blank;
+    int em = emitted[b];
+    if (is) {
+      const int n = n_sym[b];
+      sym[static_cast<size_t>(b) * sym_cap + (n < sym_cap ? n : sym_cap - 1)] = best_k;
+      n_sym[b] = n + 1;
+      ++em;
+    }
+    int tn = t;
+    if (!is || em >= max_symbols) { ++tn; em = 0; }
+    t_cur[b] = tn;
+    emitted[b] = em;
+    is_sym[b] = is ? 1 : 0;
+    label[b] = is ? best_k : 0;
+    active[b] = tn < lens[b] ? 1 : 0;
+  }
+}
+
 template <int EPI>
 void launch_slab_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmArgs& a,
                       int n_tiles, cudaStream_t s) {
@@ -846,6 +914,14 @@ void launch_joint_dw(const JointDims& d, const CUtensorMap& tm_dz_mn, const CUte
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, dw_kernel, tm_dz_mn, tm_h_mn, a);
+}
+
+void launch_greedy_step(const __nv_bfloat16* f, const float* g, const __nv_bfloat16* W, const float* bias, const int* lens,
+                        int* t_cur, int* emitted, int* n_sym, int* sym, int sym_cap, int* is_sym, int* label, int* active,
+                        int B, int Tmax, int V, int H, int blank, int max_symbols, cudaStream_t s) {
+  const size_t smem = (H + 16) * sizeof(float) + 64;
+  greedy_step_kernel<<<B, 256, smem, s>>>(f, g, W, bias, lens, t_cur, emitted, n_sym, sym, sym_cap, is_sym, label, active,
+                                         Tmax, V, H, blank, max_symbols);
 }
 
 void launch_greedy_argmax(const __nv_bfloat16* f, const __nv_bfloat16* g, const __nv_bfloat16* W, const float* bias,

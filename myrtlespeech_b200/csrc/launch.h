@@ -150,6 +150,11 @@ int max_ctas_bwd_mega(int csize);
 int bwd_mega_cooperative();   // 1 while the cooperative (co-scheduled) launch is in use
 void set_bwd_mega_cooperative(int v);
 
+// One greedy decode step with its bookkeeping (see joint.cu::greedy_step_kernel).
+void launch_greedy_step(const __nv_bfloat16* f, const float* g, const __nv_bfloat16* W, const float* bias, const int* lens,
+                        int* t_cur, int* emitted, int* n_sym, int* sym, int sym_cap, int* is_sym, int* label, int* active,
+                        int B, int Tmax, int V, int H, int blank, int max_symbols, cudaStream_t s);
+
 void set_gemm_dbg(int v);
 int read_gemm_prof(unsigned long long* out, int n);
 int smem_bytes_fwd(int nc_total);

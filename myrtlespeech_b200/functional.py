@@ -142,3 +142,16 @@ def greedy_joint_argmax(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias:
     _lib.check(lib.rnnt_greedy_joint_argmax(_ptr(f), _ptr(g), _ptr(W), _ptr(bias), _ptr(t_idx), _ptr(out),
                                             B, Tmax, V, H, _stream()))
     return out
+
+
+def greedy_step(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], lens: torch.Tensor,
+                t_cur: torch.Tensor, emitted: torch.Tensor, n_sym: torch.Tensor, sym: torch.Tensor,
+                is_sym: torch.Tensor, label: torch.Tensor, active: torch.Tensor, blank: int, max_symbols: int) -> None:
+    """One greedy decode step with its bookkeeping, in place (see ``rnnt_greedy_step`` in include/rnnt_b200.h).
+    f bf16 (B,T,H), g fp32 (B,H), W bf16 (V,H); every state tensor is int32 on the device."""
+    lib = _lib.load()
+    B, Tmax, H = f.shape
+    V = W.shape[0]
+    _lib.check(lib.rnnt_greedy_step(_ptr(f), _ptr(g), _ptr(W), _ptr(bias), _ptr(lens), _ptr(t_cur), _ptr(emitted),
+                                    _ptr(n_sym), _ptr(sym), sym.shape[1], _ptr(is_sym), _ptr(label), _ptr(active),
+                                    B, Tmax, V, H, int(blank), int(max_symbols), _stream()))

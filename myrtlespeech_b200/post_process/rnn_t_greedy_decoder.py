@@ -3,7 +3,7 @@ from typing import List
 
 import torch
 
-from ..functional import greedy_joint_argmax
+from ..functional import greedy_step
 
 
 class RNNTGreedyDecoder(torch.nn.Module):
@@ -95,42 +95,30 @@ class RNNTGreedyDecoder(torch.nn.Module):
         pred = model.prediction
 
         g0, hid0 = pred.step(None, None, B, dev)
-        g = g0.clone()
+        g = g0.float().contiguous().clone()
         hid = _clone_hidden(hid0)
-        g16 = torch.empty(B, H, dtype=torch.bfloat16, device=dev)
         cap = max(1, T * S)                                   # at most S symbols per frame
-        sym = torch.zeros(B, cap, dtype=torch.int32, device=dev)
-        n_sym = torch.zeros(B, dtype=torch.int64, device=dev)
-        t_cur = torch.zeros(B, dtype=torch.int32, device=dev)   # current frame of each utterance
-        emitted = torch.zeros(B, dtype=torch.int32, device=dev)  # symbols emitted at the current frame
-        active = t_cur < lens
-        t_idx = torch.empty(B, dtype=torch.int32, device=dev)
-        k_dev = torch.empty(B, dtype=torch.int32, device=dev)
-        minus1 = torch.full((B,), -1, dtype=torch.int32, device=dev)
-        zero = torch.zeros(B, dtype=torch.int32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        sym = torch.zeros(B, cap, **i32)
+        n_sym = torch.zeros(B, **i32)
+        t_cur = torch.zeros(B, **i32)        # current frame of each utterance
+        emitted = torch.zeros(B, **i32)      # symbols emitted at the current frame
+        is_sym = torch.zeros(B, **i32)
+        label = torch.zeros(B, **i32)
+        active = (t_cur < lens).to(torch.int32)
 
         def step():
-            t_idx.copy_(torch.where(active, t_cur, minus1))
-            g16.copy_(g)
-            greedy_joint_argmax(fb, g16, Wb, bias, t_idx, k_dev)
-            is_sym = active & (k_dev != blank)
-            # append k to the rows that emitted (masked scatter at column n_sym)
-            col = n_sym.clamp(max=cap - 1).unsqueeze(1)
-            sym.scatter_(1, col, torch.where(is_sym, k_dev, sym.gather(1, col).squeeze(1)).unsqueeze(1))
-            n_sym.add_(is_sym)
+            # joint argmax + emit / count / advance for the whole batch in one kernel (state updated in place)
+            greedy_step(fb, g, Wb, bias, lens, t_cur, emitted, n_sym, sym, is_sym, label, active, blank, S)
             # advance the prediction network only where a symbol was emitted (computed for all, selected by mask)
-            g_new, hid_new = pred.step(k_dev.clamp(min=0).long(), hid, B, dev)
-            g.copy_(torch.where(is_sym[:, None], g_new, g))
-            _update_hidden(is_sym, hid_new, hid)
-            em = torch.where(is_sym, emitted + 1, emitted)
-            advance = active & (~is_sym | (em >= S))
-            t_cur.add_(advance.to(torch.int32))
-            emitted.copy_(torch.where(advance, zero, em))
-            active.copy_(t_cur < lens)
+            m = is_sym.bool()
+            g_new, hid_new = pred.step(label.long(), hid, B, dev)
+            g.copy_(torch.where(m[:, None], g_new.float(), g))
+            _update_hidden(m, hid_new, hid)
 
         graph = None
         if self.USE_CUDA_GRAPH:
-            graph = _try_capture(step, (g, hid, sym, n_sym, t_cur, emitted, active))
+            graph = _try_capture(step, (g, hid, sym, n_sym, t_cur, emitted, active, is_sym, label))
         n = 0
         while True:
             if n % self.SYNC_EVERY == 0 and not bool(active.any()):
