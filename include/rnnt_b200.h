@@ -13,6 +13,9 @@
  *   rnnt_lattice_forward
  *       the loss alone on materialised log-probabilities (same call sites), for callers that already
  *       hold a (B,T,U+1,V) tensor.
+ *   rnnt_greedy_decode_lstm
+ *       the decoder's whole frame loop, src/myrtlespeech/post_process/ctc_greedy_decoder.py:77-92, with the recurrent
+ *       step src/myrtlespeech/model/rnn.py:133-205 of the prediction network inside it.
  *   rnnt_greedy_joint_argmax
  *       the per-step argmax of src/myrtlespeech/post_process/ctc_greedy_decoder.py:74, called from
  *       src/myrtlespeech/run/run.py:94.
@@ -96,6 +99,27 @@ int rnnt_greedy_step(const void* f, const float* g, const void* W, const float* 
                      int32_t* t_cur, int32_t* emitted, int32_t* n_sym, int32_t* sym, int sym_cap, int32_t* is_sym,
                      int32_t* label, int32_t* active, int B, int Tmax, int V, int H, int blank, int max_symbols,
                      void* stream);
+
+/* The whole greedy decode of a batch in ONE launch: prediction-network LSTM cell (single layer) + output projection +
+ * joint argmax + the emit / advance bookkeeping of rnnt_greedy_step, looped on the device until every utterance has
+ * consumed its frames (replaces the per-frame host loop of src/myrtlespeech/post_process/ctc_greedy_decoder.py:77-92
+ * and the recurrent step of src/myrtlespeech/model/rnn.py:133-205 inside it).
+ *   f          bf16 [B][Tmax][H]   encoder output           lens      DEVICE i32 [B]
+ *   W, bias    joint projection as above
+ *   gate_table f32 [V+1][4*Hp]     W_ih . emb[v] + b_ih + b_hh for every label v (torch gate order i,f,g,o);
+ *                                  row V is the start-of-sequence input
+ *   W_hh       bf16 [4*Hp][Hp]     recurrent weights (torch layout)
+ *   W_proj     bf16 [H][Hp], bias_proj f32 [H] (may be NULL): prediction output g = W_proj . h + bias_proj
+ *   sym        DEVICE i32 [B][sym_cap] emitted ids, n_sym DEVICE i32 [B] their count (sym_cap >= Tmax*max_symbols holds all)
+ * Arithmetic: h and W_* enter the tensor cores as bf16 with fp32 accumulation; the cell state c and the gate
+ * non-linearities are fp32; g is rounded to bf16 before tanh(f + g) exactly as in rnnt_greedy_step.
+ * rnnt_greedy_decode_workspace_bytes returns 0 when the shape is not covered (Hp % 8, H % 8, slices that do not fit the
+ * shared memory of the co-resident CTAs); callers then use rnnt_greedy_step. */
+size_t rnnt_greedy_decode_workspace_bytes(int B, int V, int H, int Hp);
+int rnnt_greedy_decode_lstm(const void* f, const int32_t* lens, const void* W, const float* bias,
+                            const float* gate_table, const void* W_hh, const void* W_proj, const float* bias_proj,
+                            int B, int Tmax, int V, int H, int Hp, int blank, int max_symbols, int32_t* sym,
+                            int sym_cap, int32_t* n_sym, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Debug / test hooks (not part of the drop-in surface). */
 int rnnt_debug_copy_stats(const void* workspace, int B, int Tmax, int Umax, int V, int H, float* lp_blank,

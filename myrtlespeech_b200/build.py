@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "librnnt_b200.so")
-SOURCES = ["capi.cu", "joint.cu", "persist.cu", "lattice.cu"]
+SOURCES = ["capi.cu", "joint.cu", "persist.cu", "lattice.cu", "decode.cu"]
 HEADERS = ["ptx.cuh", "common.cuh", "launch.h", os.path.join("..", "..", "include", "rnnt_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <utility>
 #include <vector>
 
@@ -226,6 +227,61 @@ int count_tiles(const int32_t* fl, const int32_t* yl, int B) {
   return n;
 }
 
+// ---- greedy decode (decode.cu): N-split of the three per-step GEMMs over the co-resident CTAs ----------------------
+struct DecPlan {
+  int ok;
+  int Bp, nJ, nslJ, kbJ, nu, nL, nslL, kbL, nP, nslP, kbP, n_stages;
+  int o_wj, o_wl, o_wp, o_c, o_h, o_g, o_state, o_bars, smem;
+  size_t w_gbar, w_amax, w_hj, w_hbuf, w_whh, w_total;
+};
+
+int slice16(int n_total, int G) {  // smallest multiple of 16 that covers n_total with at most G slices
+  int n = 16;
+  while ((n_total + n - 1) / n > G) n += 16;
+  return n;
+}
+
+DecPlan make_dec_plan(int B, int V, int H, int Hp) {
+  DecPlan d{};
+  if (B < 1 || B > 2048 || V < 1 || H < 8 || H % 8 || Hp < 8 || Hp % 8) return d;
+  const int G = sm_count();
+  d.Bp = static_cast<int>(align_up(B, 128));
+  d.nJ = slice16(V, G); d.nslJ = (V + d.nJ - 1) / d.nJ; d.kbJ = (H + 63) / 64;
+  d.nP = slice16(H, G); d.nslP = (H + d.nP - 1) / d.nP; d.kbP = (Hp + 63) / 64;
+  d.nu = 4;
+  while ((Hp + d.nu - 1) / d.nu > G) d.nu += 4;
+  d.nL = 4 * d.nu; d.nslL = (Hp + d.nu - 1) / d.nu; d.kbL = (Hp + 63) / 64;
+  if (d.nJ > 256 || d.nP > 256 || d.nL > 256) return d;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return static_cast<int>(r); };
+  d.o_wj = take(static_cast<size_t>(d.kbJ) * d.nJ * 128);
+  d.o_wl = take(static_cast<size_t>(d.kbL) * d.nL * 128);
+  d.o_wp = take(static_cast<size_t>(d.kbP) * d.nP * 128);
+  d.o_c = take(sizeof(float) * d.Bp * d.nu);
+  d.o_h = take(2 * static_cast<size_t>(d.Bp) * d.nu);
+  d.o_g = take(sizeof(float) * d.Bp * d.nP);
+  d.o_state = take(sizeof(int) * 5 * B);
+  d.o_bars = take(256);
+  const size_t fixed = o + 1024;  // + alignment slack
+  const size_t cap = 227 * 1024;
+  if (fixed + 2 * 16384 > cap) return d;
+  d.n_stages = static_cast<int>((cap - fixed) / 16384);
+  if (d.n_stages > 8) d.n_stages = 8;
+  const int ring = d.n_stages * 16384;  // the ring sits first (1024-aligned stages)
+  d.o_wj += ring; d.o_wl += ring; d.o_wp += ring; d.o_c += ring; d.o_h += ring; d.o_g += ring; d.o_state += ring; d.o_bars += ring;
+  d.smem = static_cast<int>(fixed) + ring;
+  size_t w = 0;
+  auto wtake = [&](size_t bytes) { size_t r = w; w = align_up(w + bytes, 1024); return r; };
+  d.w_gbar = wtake(1024);
+  d.w_amax = wtake(sizeof(unsigned long long) * 2 * d.Bp);
+  d.w_hj = wtake(2 * static_cast<size_t>(d.Bp) * H);
+  d.w_hbuf = wtake(2 * static_cast<size_t>(2) * d.Bp * Hp);
+  d.w_whh = wtake(2 * static_cast<size_t>(d.nslL) * d.nL * Hp);
+  d.w_total = w;
+  d.ok = 1;
+  return d;
+}
+
 }  // namespace
 
 extern "C" {
@@ -239,6 +295,7 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "time_kernels")) g_time_kernels = value != 0;
   if (!strcmp(key, "gemm_dbg")) set_gemm_dbg(value);
   if (!strcmp(key, "path")) g_path = value;
+  if (!strcmp(key, "decode_cooperative")) set_decode_cooperative(value);
   if (!strcmp(key, "mega_cooperative")) set_bwd_mega_cooperative(value);  // 0: plain launch (ncu cannot replay cooperative launches)
   if (!strcmp(key, "cluster") && (value == 2 || value == 4)) g_cluster = value;
   if (!strcmp(key, "cluster_bwd") && (value == 2 || value == 4)) g_cluster_bwd = value;
@@ -520,6 +577,60 @@ int rnnt_greedy_step(const void* f, const float* g, const void* W, const float* 
           launch_greedy_step(static_cast<const __nv_bfloat16*>(f), g, static_cast<const __nv_bfloat16*>(W), bias, lens, t_cur,
                              emitted, n_sym, sym, sym_cap, is_sym, label, active, B, Tmax, V, H, blank, max_symbols,
                              static_cast<cudaStream_t>(stream)));
+  CUDA_TRY(cudaGetLastError());
+  return RNNT_OK;
+}
+
+size_t rnnt_greedy_decode_workspace_bytes(int B, int V, int H, int Hp) {
+  const DecPlan d = make_dec_plan(B, V, H, Hp);
+  return d.ok ? d.w_total : 0;
+}
+
+int rnnt_greedy_decode_lstm(const void* f, const int32_t* lens, const void* W, const float* bias, const float* gate_table,
+                            const void* W_hh, const void* W_proj, const float* bias_proj, int B, int Tmax, int V, int H,
+                            int Hp, int blank, int max_symbols, int32_t* sym, int sym_cap, int32_t* n_sym, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (B < 1 || Tmax < 1 || V < 1 || sym_cap < 1 || max_symbols < 1)
+    return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d V=%d sym_cap=%d max_symbols=%d out of range", B, Tmax, V, sym_cap, max_symbols);
+  if (blank < 0 || blank >= V) return fail(RNNT_ERR_INVALID_ARGUMENT, "blank=%d must be in [0, %d]", blank, V - 1);
+  if (!f || !lens || !W || !gate_table || !W_hh || !W_proj || !sym || !n_sym || !workspace)
+    return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+  const DecPlan d = make_dec_plan(B, V, H, Hp);
+  if (!d.ok) return fail(RNNT_ERR_UNSUPPORTED, "fused greedy decode does not cover B=%d V=%d H=%d Hp=%d", B, V, H, Hp);
+  if (workspace_bytes < d.w_total)
+    return fail(RNNT_ERR_WORKSPACE_TOO_SMALL, "workspace %zu < %zu bytes", workspace_bytes, d.w_total);
+  const int G = max_ctas_greedy_decode(d.smem);
+  if (G < d.nslJ || G < d.nslL || G < d.nslP)
+    return fail(RNNT_ERR_UNSUPPORTED, "fused greedy decode needs %d co-resident CTAs, the device offers %d",
+                std::max(d.nslJ, std::max(d.nslL, d.nslP)), G);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  CUDA_TRY(cudaMemsetAsync(ws, 0, d.w_whh, s));  // barrier counter, argmax keys, hj, both h buffers (h_0 = 0)
+  __nv_bfloat16* whh_perm = reinterpret_cast<__nv_bfloat16*>(ws + d.w_whh);
+  KLAUNCH(K_MISC, s, launch_permute_whh(static_cast<const __nv_bfloat16*>(W_hh), whh_perm, Hp, d.nu, d.nslL * d.nL, s));
+  CUtensorMap tm_hj, tm_hbuf, tm_wj, tm_wl, tm_wp;
+  int rc;
+  if ((rc = make_map(&tm_hj, ws + d.w_hj, H, d.Bp, H, 64, 128))) return rc;
+  if ((rc = make_map(&tm_hbuf, ws + d.w_hbuf, Hp, 2 * static_cast<uint64_t>(d.Bp), Hp, 64, 128))) return rc;
+  if ((rc = make_map(&tm_wj, W, H, V, H, 64, d.nJ))) return rc;
+  if ((rc = make_map(&tm_wl, whh_perm, Hp, static_cast<uint64_t>(d.nslL) * d.nL, Hp, 64, d.nL))) return rc;
+  if ((rc = make_map(&tm_wp, W_proj, Hp, H, Hp, 64, d.nP))) return rc;
+  DecodeArgs a{};
+  a.B = B; a.Bp = d.Bp; a.Tmax = Tmax; a.V = V; a.H = H; a.Hp = Hp; a.blank = blank; a.S = max_symbols; a.sym_cap = sym_cap;
+  a.max_steps = Tmax * max_symbols + 1;
+  a.nJ = d.nJ; a.nslJ = d.nslJ; a.kbJ = d.kbJ; a.nu = d.nu; a.nL = d.nL; a.nslL = d.nslL; a.kbL = d.kbL;
+  a.nP = d.nP; a.nslP = d.nslP; a.kbP = d.kbP; a.n_stages = d.n_stages;
+  a.o_wj = d.o_wj; a.o_wl = d.o_wl; a.o_wp = d.o_wp; a.o_c = d.o_c; a.o_h = d.o_h; a.o_g = d.o_g; a.o_state = d.o_state;
+  a.o_bars = d.o_bars;
+  a.f = static_cast<const __nv_bfloat16*>(f); a.lens = lens; a.bias_j = bias; a.table = gate_table; a.bias_p = bias_proj;
+  a.hj = reinterpret_cast<__nv_bfloat16*>(ws + d.w_hj);
+  a.hbuf = reinterpret_cast<__nv_bfloat16*>(ws + d.w_hbuf);
+  a.amax = reinterpret_cast<unsigned long long*>(ws + d.w_amax);
+  a.gbar = reinterpret_cast<unsigned*>(ws + d.w_gbar);
+  a.sym = sym; a.n_sym = n_sym;
+  cudaError_t e = cudaSuccess;
+  KLAUNCH(K_MISC, s, e = launch_greedy_decode(tm_hj, tm_hbuf, tm_wj, tm_wl, tm_wp, a, G, d.smem, s));
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(RNNT_ERR_CUDA, "greedy decode launch -> %s", cudaGetErrorString(e)); }
   CUDA_TRY(cudaGetLastError());
   return RNNT_OK;
 }

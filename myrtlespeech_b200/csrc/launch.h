@@ -155,6 +155,35 @@ void launch_greedy_step(const __nv_bfloat16* f, const float* g, const __nv_bfloa
                         int* t_cur, int* emitted, int* n_sym, int* sym, int sym_cap, int* is_sym, int* label, int* active,
                         int B, int Tmax, int V, int H, int blank, int max_symbols, cudaStream_t s);
 
+
+// ---- decode.cu --------------------------------------------------------------------------------
+// Whole greedy decode loop (LSTM prediction cell + projection + joint argmax + bookkeeping) in one cooperative launch.
+struct DecodeArgs {
+  int B, Bp, Tmax, V, H, Hp, blank, S, sym_cap, max_steps;
+  int nJ, nslJ, kbJ;       // joint:      vocabulary rows per CTA, CTAs with a slice, k-blocks over H
+  int nu, nL, nslL, kbL;   // LSTM cell:  hidden units per CTA, nL = 4 nu gate rows, slices, k-blocks over Hp
+  int nP, nslP, kbP;       // projection: output columns per CTA, slices, k-blocks over Hp
+  int n_stages;            // activation ring depth (16 KB stages)
+  int o_wj, o_wl, o_wp, o_c, o_h, o_g, o_state, o_bars;  // shared-memory offsets from the 1024-aligned base
+  const __nv_bfloat16* f;  // [B][Tmax][H]
+  const int* lens;         // [B] device
+  const float* bias_j;     // [V] or null
+  const float* table;      // [V+1][4 Hp]  W_ih . emb[v] + b_ih + b_hh, torch gate order i f g o; row V = start of sequence
+  const float* bias_p;     // [H] or null
+  __nv_bfloat16* hj;       // [Bp][H]      bf16(tanh(f[b, t_b] + g[b]))
+  __nv_bfloat16* hbuf;     // [2][Bp][Hp]  hidden state, double buffered
+  unsigned long long* amax;  // [2][Bp]    packed (ordered logit, ~index) argmax keys
+  unsigned* gbar;          // grid barrier counter
+  int* sym;                // [B][sym_cap]
+  int* n_sym;              // [B]
+};
+void launch_permute_whh(const __nv_bfloat16* W, __nv_bfloat16* out, int Hp, int nu, int n_rows, cudaStream_t s);
+int max_ctas_greedy_decode(int smem_bytes);
+cudaError_t launch_greedy_decode(const CUtensorMap& tm_hj, const CUtensorMap& tm_hbuf, const CUtensorMap& tm_wj,
+                                 const CUtensorMap& tm_wl, const CUtensorMap& tm_wp, const DecodeArgs& a, int n_ctas,
+                                 int smem_bytes, cudaStream_t s);
+void set_decode_cooperative(int v);
+
 void set_gemm_dbg(int v);
 int read_gemm_prof(unsigned long long* out, int n);
 int smem_bytes_fwd(int nc_total);

@@ -3,7 +3,7 @@ from typing import List
 
 import torch
 
-from ..functional import greedy_step
+from ..functional import greedy_decode_lstm, greedy_decode_lstm_supported, greedy_step
 
 
 class RNNTGreedyDecoder(torch.nn.Module):
@@ -71,6 +71,9 @@ class RNNTGreedyDecoder(torch.nn.Module):
         finally:
             model.train(was_training)
 
+    #: run the whole loop (LSTM cell + projection + joint argmax + bookkeeping) as ONE launch when the prediction network
+    #: is a single-layer LSTM (``rnnt_greedy_decode_lstm``); otherwise one CUDA graph per step
+    USE_FUSED_LOOP = True
     #: decode steps enqueued between two host checks of "is any utterance still active"
     SYNC_EVERY = 32
     #: replay one captured CUDA graph per decode step instead of ~20 eager launches (falls back to eager launches
@@ -93,6 +96,13 @@ class RNNTGreedyDecoder(torch.nn.Module):
         bias = None if bias is None else bias.detach().float().contiguous()
         lens = lengths.to(dev, torch.int32)
         pred = model.prediction
+        if self.USE_FUSED_LOOP and T > 0:
+            packed = _pack_lstm_prediction(pred, B, Wb.size(0), H)
+            if packed is not None:
+                table, whh, wproj, bproj = packed
+                sym, n_sym = greedy_decode_lstm(fb, lens.contiguous(), Wb, bias, table, whh, wproj, bproj, blank, S)
+                sym_h, n_h = sym.cpu(), n_sym.cpu().tolist()
+                return [sym_h[b, : n_h[b]].tolist() for b in range(B)]
 
         g0, hid0 = pred.step(None, None, B, dev)
         g = g0.float().contiguous().clone()
@@ -133,6 +143,31 @@ class RNNTGreedyDecoder(torch.nn.Module):
 
     def extra_repr(self) -> str:
         return f"blank_index={self.blank_index}, max_symbols_per_step={self.max_symbols_per_step}"
+
+
+def _pack_lstm_prediction(pred, B: int, V: int, H: int):
+    """``(gate_table, W_hh, W_proj, b_proj)`` for the one-launch decode, or None if ``pred`` is not an embedding +
+    single-layer unidirectional LSTM + projection (``RNNTPredictionNet`` layout) the fused kernel covers.
+
+    ``gate_table[v] = W_ih . emb[v] + b_ih + b_hh`` (fp32) folds the embedding lookup and the input half of the cell
+    into one row gather per emitted label; row ``vocab_size`` is the start-of-sequence input."""
+    emb, rnn, proj = getattr(pred, "embedding", None), getattr(pred, "rnn", None), getattr(pred, "proj", None)
+    if not (isinstance(emb, torch.nn.Embedding) and isinstance(rnn, torch.nn.LSTM) and isinstance(proj, torch.nn.Linear)):
+        return None
+    if rnn.num_layers != 1 or rnn.bidirectional or getattr(rnn, "proj_size", 0) != 0:
+        return None
+    if emb.num_embeddings != V + 1 or proj.out_features != H or not emb.weight.is_cuda:
+        return None
+    Hp = rnn.hidden_size
+    if not greedy_decode_lstm_supported(B, V, H, Hp):
+        return None
+    table = emb.weight.detach().float() @ rnn.weight_ih_l0.detach().float().t()
+    if rnn.bias:
+        table = table + (rnn.bias_ih_l0.detach().float() + rnn.bias_hh_l0.detach().float())
+    whh = rnn.weight_hh_l0.detach().to(torch.bfloat16).contiguous()
+    wproj = proj.weight.detach().to(torch.bfloat16).contiguous()
+    bproj = None if proj.bias is None else proj.bias.detach().float().contiguous()
+    return table.contiguous(), whh, wproj, bproj
 
 
 def _clone_hidden(h):

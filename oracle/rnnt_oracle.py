@@ -271,13 +271,17 @@ def greedy_decode(
     blank: int,
     max_symbols_per_step: int,
     faithful: bool = False,
+    per_utterance_margin: bool = False,
 ) -> Tuple[List[List[int]], float]:
     """RNN-T greedy search for each utterance.
 
     ``pred_step(label_or_None, state) -> (g_vec (H,), new_state)`` is the
     prediction network; ``None`` is the start-of-sequence input.  Returns the
     transcripts and the smallest top-2 logit margin seen (so tests can tell a
-    genuine mismatch from an argmax tie within accumulation noise).
+    genuine mismatch from an argmax tie within accumulation noise); with
+    ``per_utterance_margin`` the second value is the list of per-utterance
+    minima instead (utterances are independent, so a near-tie only excuses the
+    utterance it occurs in).
 
     Ties resolve to the lowest index (numpy/torch argmax semantics).
     """
@@ -287,8 +291,10 @@ def greedy_decode(
     b_ = np.zeros(V) if bias is None else np.asarray(bias, dtype=np.float64)
     out: List[List[int]] = []
     min_margin = np.inf
+    margins: List[float] = []
     for b in range(f.shape[0]):
         hyp: List[int] = []
+        min_margin = np.inf if per_utterance_margin else min_margin
         g, state = pred_step(None, None)
         for t in range(int(f_lens[b])):
             for _ in range(max_symbols_per_step):
@@ -307,4 +313,66 @@ def greedy_decode(
                 hyp.append(k)
                 g, state = pred_step(k, state)
         out.append(hyp)
+        margins.append(float(min_margin))
+    if per_utterance_margin:
+        return out, margins
     return out, float(min_margin)
+
+
+# --------------------------------------------------------------------------- #
+# prediction network step (embedding + single-layer LSTM + projection)
+# --------------------------------------------------------------------------- #
+def lstm_pred_step(
+    emb: np.ndarray,
+    w_ih: np.ndarray,
+    w_hh: np.ndarray,
+    b_ih: Optional[np.ndarray],
+    b_hh: Optional[np.ndarray],
+    w_proj: np.ndarray,
+    b_proj: Optional[np.ndarray],
+    faithful: bool = False,
+) -> Callable[[Optional[int], object], Tuple[np.ndarray, object]]:
+    """Returns the ``pred_step`` callback of :func:`greedy_decode` for an embedding (V+1, E; row V = start of
+    sequence) + LSTM cell (torch gate order i, f, g, o; follows the cell of ``torch.nn.LSTM`` that
+    ``src/myrtlespeech/model/rnn.py:133-205`` wraps) + linear projection to the joint width.
+
+    ``faithful=True`` rounds where the one-launch CUDA decode rounds: the input half ``W_ih . emb[v] + b`` is an fp32
+    table, ``h`` and ``W_hh`` / ``W_proj`` are bf16 operands of an fp32-accumulating product, ``c`` stays fp32 and the
+    projected ``g`` is rounded to bf16.
+    """
+    emb = np.asarray(emb, dtype=np.float64)
+    w_ih = np.asarray(w_ih, dtype=np.float64)
+    w_hh = np.asarray(w_hh, dtype=np.float64)
+    w_proj = np.asarray(w_proj, dtype=np.float64)
+    hp = w_hh.shape[1]
+    bias = np.zeros(4 * hp)
+    if b_ih is not None:
+        bias = bias + np.asarray(b_ih, dtype=np.float64)
+    if b_hh is not None:
+        bias = bias + np.asarray(b_hh, dtype=np.float64)
+    table = emb @ w_ih.T + bias
+    if faithful:
+        table = table.astype(np.float32).astype(np.float64)
+        w_hh = bf16_round(w_hh)
+        w_proj = bf16_round(w_proj)
+    bp = np.zeros(w_proj.shape[0]) if b_proj is None else np.asarray(b_proj, dtype=np.float64)
+    sos = emb.shape[0] - 1
+
+    def sigmoid(x):
+        return 1.0 / (1.0 + np.exp(-x))
+
+    def step(label: Optional[int], state):
+        h, c = (np.zeros(hp), np.zeros(hp)) if state is None else state
+        a = table[sos if label is None else int(label)] + w_hh @ h
+        i, f, g, o = a[:hp], a[hp:2 * hp], a[2 * hp:3 * hp], a[3 * hp:]
+        c = sigmoid(f) * c + sigmoid(i) * np.tanh(g)
+        h = sigmoid(o) * np.tanh(c)
+        if faithful:
+            c = c.astype(np.float32).astype(np.float64)
+            h = bf16_round(h)
+        out = w_proj @ h + bp
+        if faithful:
+            out = bf16_round(out)
+        return out, (h, c)
+
+    return step

@@ -1,5 +1,6 @@
 """BASELINE.json configs[4]: greedy decode over the fused joint, B=128 T=500 V=H=1024 max-symbols-per-step=4.
-Random-init LSTM prediction network (there is no checkpoint); reports utterances/s and joint steps/s."""
+Random-init LSTM prediction network (there is no checkpoint); reports utterances/s for the one-launch decode
+(rnnt_greedy_decode_lstm) and for the per-step CUDA-graph loop, CUDA-event timed around the decoder call."""
 import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,16 +8,30 @@ from myrtlespeech_b200.model import RNNTJoint
 from myrtlespeech_b200.model.rnn_t import RNNT, RNNTPredictionNet
 from myrtlespeech_b200.post_process import RNNTGreedyDecoder
 B, T, V, H, S = 128, 500, 1024, 1024, 4
+E, HP = int(os.environ.get("PRED_E", 256)), int(os.environ.get("PRED_H", 512))
+BLANK_BIAS = float(os.environ.get("BLANK_BIAS", 0.0))
 torch.manual_seed(0)
 joint = RNNTJoint(H, V)
-pred = RNNTPredictionNet(V, 256, 512, 1, H)
+pred = RNNTPredictionNet(V, E, HP, 1, H)
+with torch.no_grad():
+    joint.fc.bias[V - 1] += BLANK_BIAS
 model = RNNT(torch.nn.Identity(), pred, joint).cuda()
 dec = RNNTGreedyDecoder(V - 1, model, max_symbols_per_step=S)
 f = torch.randn(B, T, H, device="cuda").bfloat16()
 lens = torch.full((B,), T, dtype=torch.int32)
-for it in range(3):
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    out = dec(f, lens)
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    n_sym = sum(len(o) for o in out)
-    print(f"decode pass {it}: {dt*1e3:.1f} ms, {B/dt:.1f} utt/s, {n_sym} symbols emitted ({n_sym/B/T:.2f} per frame)", flush=True)
+outs = {}
+for fused in (True, False):
+    dec.USE_FUSED_LOOP = fused
+    for it in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); t0 = time.perf_counter(); e0.record()
+        out = dec(f, lens)
+        e1.record(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        n_sym = sum(len(o) for o in out)
+        steps = max(len(o) for o in out) + T
+        print(f"{'one-launch' if fused else 'graph-step'} pass {it}: wall {dt*1e3:.1f} ms (device {e0.elapsed_time(e1):.1f} ms), "
+              f"{B/dt:.1f} utt/s, {n_sym} symbols ({n_sym/B/T:.2f} per frame), <= {steps} steps "
+              f"-> {e0.elapsed_time(e1)*1e3/steps:.1f} us/step", flush=True)
+    outs[fused] = out
+same = sum(a == b for a, b in zip(outs[True], outs[False]))
+print(f"transcripts identical between the two paths (bf16 LSTM vs cuDNN fp32 LSTM): {same}/{B}")

@@ -94,3 +94,78 @@ def test_greedy_decoder_constructed_path():
     dec = RNNTGreedyDecoder(blank, model, max_symbols_per_step=3)
     assert dec(f.cuda(), torch.tensor([4])) == [[2]]
     assert dec(f.cuda(), torch.tensor([0])) == [[]]
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# one-launch decode: LSTM prediction cell + projection + joint argmax + bookkeeping looped on the device
+# --------------------------------------------------------------------------------------------------------------------
+def _lstm_case(seed, B, T, V, H, Hp, E, lens=None, blank_bias=2.5):
+    """Seeded model + inputs (CPU generator, so the GPU box and the CPU container see the same numbers)."""
+    torch.manual_seed(seed)
+    joint = RNNTJoint(H, V)
+    pred = RNNTPredictionNet(V, E, Hp, 1, H)
+    with torch.no_grad():
+        joint.fc.weight.mul_(4.0)   # spread the logits so that argmax margins are far above bf16 noise
+        pred.proj.weight.mul_(3.0)
+        joint.fc.bias[V - 1] += blank_bias  # a realistic share of blank steps (frame advances)
+        for prm in list(joint.parameters()) + list(pred.parameters()):
+            prm.copy_(prm.bfloat16().float())  # bf16-representable weights: the oracle and the kernel see the same values
+    f = (torch.randn(B, T, H) * 1.5).bfloat16()
+    if lens is None:
+        lens = torch.randint(0, T + 1, (B,), dtype=torch.int32)
+        lens[0] = T
+    return joint, pred, f, lens
+
+
+def _oracle_transcripts(joint, pred, f, lens, blank, S):
+    n = lambda t: None if t is None else t.detach().cpu().float().numpy()  # noqa: E731
+    step = O.lstm_pred_step(n(pred.embedding.weight), n(pred.rnn.weight_ih_l0), n(pred.rnn.weight_hh_l0),
+                            n(pred.rnn.bias_ih_l0), n(pred.rnn.bias_hh_l0), n(pred.proj.weight), n(pred.proj.bias),
+                            faithful=True)
+    return O.greedy_decode(f.float().numpy(), lens.numpy(), n(joint.fc.weight), n(joint.fc.bias), step, blank, S,
+                           faithful=True, per_utterance_margin=True)
+
+
+MARGIN = 4e-3
+LSTM_CASES = [
+    # seed, B, T, V, H, Hp, E, S
+    (3, 5, 23, 40, 64, 64, 32, 1),
+    (3, 5, 23, 40, 64, 64, 32, 4),
+    (1, 7, 17, 29, 128, 72, 16, 2),     # chars vocabulary, Hp not a multiple of 64 (zero-filled k-block tail)
+    (2, 130, 9, 300, 192, 200, 24, 2),  # two batch tiles, several vocabulary / unit slices per phase
+]
+
+
+@pytest.mark.parametrize("seed,B,T,V,H,Hp,E,S", LSTM_CASES)
+def test_fused_lstm_decode_matches_oracle(seed, B, T, V, H, Hp, E, S):
+    joint, pred, f, lens = _lstm_case(seed, B, T, V, H, Hp, E)
+    blank = V - 1
+    want, margins = _oracle_transcripts(joint, pred, f, lens, blank, S)
+    # utterances are independent: one whose smallest top-2 logit margin is within bf16 / tanh.approx noise is excused
+    clear = [m > MARGIN for m in margins]
+    assert sum(clear) >= 0.6 * B, "seed produced too many near-ties; pick another"
+    model = RNNT(torch.nn.Identity(), pred, joint).cuda()
+    dec = RNNTGreedyDecoder(blank, model, max_symbols_per_step=S)
+    calls = []
+    import myrtlespeech_b200.post_process.rnn_t_greedy_decoder as D
+    orig = D.greedy_decode_lstm
+    D.greedy_decode_lstm = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        got = dec(f.cuda(), lens)
+    finally:
+        D.greedy_decode_lstm = orig
+    assert calls, "the one-launch decode was not taken"
+    assert [g for g, c in zip(got, clear) if c] == [w for w, c in zip(want, clear) if c]
+    assert any(len(s) > 0 for s in got)
+    assert all(len(g) <= int(l) * S for g, l in zip(got, lens))
+
+
+def test_fused_lstm_decode_is_deterministic_and_handles_empty_batch_rows():
+    joint, pred, f, _ = _lstm_case(3, 6, 11, 40, 64, 64, 32)
+    lens = torch.tensor([11, 0, 5, 0, 1, 11], dtype=torch.int32)
+    model = RNNT(torch.nn.Identity(), pred, joint).cuda()
+    dec = RNNTGreedyDecoder(39, model, max_symbols_per_step=3)
+    a = dec(f.cuda(), lens)
+    b = dec(f.cuda(), lens)
+    assert a == b
+    assert a[1] == [] and a[3] == []

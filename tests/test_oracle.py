@@ -160,3 +160,33 @@ def test_greedy_decode_constructed():
     # after the first emission the veto stays on (pred ignores history), so only the first symbol appears
     assert hyp == [[2]]
     assert margin > 0
+
+
+def test_lstm_pred_step_matches_torch_lstm():
+    """The oracle's prediction-network step (embedding + LSTM cell + projection) against torch.nn.LSTM -- the module
+    the reference's RNN wrapper builds (src/myrtlespeech/model/rnn.py:133-205) -- fed one label at a time."""
+    import torch
+    from myrtlespeech_b200.model.rnn_t import RNNTPredictionNet
+
+    torch.manual_seed(0)
+    V, E, Hp, H = 11, 6, 8, 10
+    pred = RNNTPredictionNet(V, E, Hp, 1, H).cpu().double()
+    n = lambda t: t.detach().numpy()  # noqa: E731
+    step = O.lstm_pred_step(n(pred.embedding.weight), n(pred.rnn.weight_ih_l0), n(pred.rnn.weight_hh_l0),
+                            n(pred.rnn.bias_ih_l0), n(pred.rnn.bias_hh_l0), n(pred.proj.weight), n(pred.proj.bias))
+    labels = [None, 3, 0, 10, 7, 7]
+    state, hx = None, None
+    for lab in labels:
+        got, state = step(lab, state)
+        tl = None if lab is None else torch.tensor([lab])
+        want, hx = pred.step(tl, hx, 1, torch.device("cpu"))
+        np.testing.assert_allclose(got, want[0].detach().numpy(), rtol=1e-10, atol=1e-12)
+    # bf16-faithful variant stays close to the exact one (it only moves rounding points)
+    fstep = O.lstm_pred_step(n(pred.embedding.weight), n(pred.rnn.weight_ih_l0), n(pred.rnn.weight_hh_l0),
+                             n(pred.rnn.bias_ih_l0), n(pred.rnn.bias_hh_l0), n(pred.proj.weight), n(pred.proj.bias),
+                             faithful=True)
+    s1 = s2 = None
+    for lab in labels:
+        a, s1 = step(lab, s1)
+        b, s2 = fstep(lab, s2)
+        assert np.max(np.abs(a - b)) < 3e-2
