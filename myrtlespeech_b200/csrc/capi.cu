@@ -282,6 +282,55 @@ DecPlan make_dec_plan(int B, int V, int H, int Hp) {
   return d;
 }
 
+// Cluster variant of the decode (decode.cu): rows of each weight matrix split over the C CTAs of a cluster.
+struct CDecPlan {
+  int ok;
+  int C, RJ, RP, up, mtJ, mtP, mtL, kbH, kbHp, n_stages, tmem_cols;
+  int o_hj, o_h0, o_h1, o_gates, o_c, o_hown, o_amax, o_part, o_state, o_bars, smem;
+  size_t w_whh, w_total;
+};
+
+CDecPlan make_cdec_plan(int B, int V, int H, int Hp, int C) {
+  CDecPlan d{};
+  if (B < 1 || V < 1 || H < 8 || H % 8 || Hp < 8 || Hp % 8 || C < 1 || C > 16) return d;
+  auto up64 = [](int x) { return (x + 63) / 64 * 64; };
+  d.C = C;
+  d.up = up64((Hp + C - 1) / C); d.RP = up64((H + C - 1) / C); d.RJ = up64((V + C - 1) / C);
+  d.mtL = d.up / 32; d.mtP = (d.RP + 127) / 128; d.mtJ = (d.RJ + 127) / 128;
+  if (d.mtL + d.mtP + d.mtJ > 10) return d;
+  d.kbH = (H + 63) / 64; d.kbHp = (Hp + 63) / 64;
+  d.tmem_cols = 32;
+  while (d.tmem_cols < 16 * (d.mtL + d.mtP + d.mtJ)) d.tmem_cols *= 2;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return static_cast<int>(r); };
+  d.o_hj = take(static_cast<size_t>(C) * d.RP / 64 * 2048);
+  d.o_h0 = take(static_cast<size_t>(C) * d.up / 64 * 2048);
+  d.o_h1 = take(static_cast<size_t>(C) * d.up / 64 * 2048);
+  d.o_gates = take(4 * 32 * 16 * sizeof(float));
+  d.o_c = take(static_cast<size_t>(d.up) * 16 * sizeof(float));
+  d.o_hown = take(static_cast<size_t>(d.up) * 16 * 2);
+  d.o_amax = take(static_cast<size_t>(C) * 16 * 8);
+  d.o_part = take(4 * 16 * 8);
+  d.o_state = take(512);
+  d.o_bars = take(512);
+  const size_t fixed = o + 1024, cap = 227 * 1024;
+  if (fixed + 3 * 16384 > cap) return d;
+  d.n_stages = static_cast<int>((cap - fixed) / 16384);
+  if (d.n_stages > 8) d.n_stages = 8;
+  const int ring = d.n_stages * 16384;
+  d.o_hj += ring; d.o_h0 += ring; d.o_h1 += ring; d.o_gates += ring; d.o_c += ring; d.o_hown += ring; d.o_amax += ring;
+  d.o_part += ring; d.o_state += ring; d.o_bars += ring;
+  d.smem = static_cast<int>(fixed) + ring;
+  d.w_whh = 0;
+  d.w_total = align_up(2 * static_cast<size_t>(C) * 4 * d.up * Hp, 1024);
+  d.ok = 1;
+  return d;
+}
+
+int g_decode_variant = 1;  // 1: one cluster per 16 utterances (default); 0: N-split over the grid with grid barriers
+int g_decode_cluster = 8;
+int g_decode_prof = 0;
+
 }  // namespace
 
 extern "C" {
@@ -296,6 +345,9 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "gemm_dbg")) set_gemm_dbg(value);
   if (!strcmp(key, "path")) g_path = value;
   if (!strcmp(key, "decode_cooperative")) set_decode_cooperative(value);
+  if (!strcmp(key, "decode_prof")) g_decode_prof = value;
+  if (!strcmp(key, "decode_variant") && (value == 0 || value == 1)) g_decode_variant = value;
+  if (!strcmp(key, "decode_cluster") && value >= 1 && value <= 16) g_decode_cluster = value;
   if (!strcmp(key, "mega_cooperative")) set_bwd_mega_cooperative(value);  // 0: plain launch (ncu cannot replay cooperative launches)
   if (!strcmp(key, "cluster") && (value == 2 || value == 4)) g_cluster = value;
   if (!strcmp(key, "cluster_bwd") && (value == 2 || value == 4)) g_cluster_bwd = value;
@@ -317,6 +369,8 @@ long long rnnt_debug_get(const char* key) {
   if (!strcmp(key, "max_ctas_mega_c4")) return max_ctas_bwd_mega(4);
   return -1;
 }
+
+int rnnt_debug_decode_prof(unsigned long long* out, int n) { return read_decode_prof(out, n); }
 
 int rnnt_debug_read_prof(unsigned long long* out, int n) { return g_path == 1 ? read_persist_prof(out, n) : read_gemm_prof(out, n); }
 
@@ -583,7 +637,9 @@ int rnnt_greedy_step(const void* f, const float* g, const void* W, const float* 
 
 size_t rnnt_greedy_decode_workspace_bytes(int B, int V, int H, int Hp) {
   const DecPlan d = make_dec_plan(B, V, H, Hp);
-  return d.ok ? d.w_total : 0;
+  const CDecPlan c = make_cdec_plan(B, V, H, Hp, g_decode_cluster);
+  const size_t a = d.ok ? d.w_total : 0, b = c.ok ? c.w_total : 0;
+  return a > b ? a : b;
 }
 
 int rnnt_greedy_decode_lstm(const void* f, const int32_t* lens, const void* W, const float* bias, const float* gate_table,
@@ -595,6 +651,33 @@ int rnnt_greedy_decode_lstm(const void* f, const int32_t* lens, const void* W, c
   if (blank < 0 || blank >= V) return fail(RNNT_ERR_INVALID_ARGUMENT, "blank=%d must be in [0, %d]", blank, V - 1);
   if (!f || !lens || !W || !gate_table || !W_hh || !W_proj || !sym || !n_sym || !workspace)
     return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const CDecPlan c = make_cdec_plan(B, V, H, Hp, g_decode_cluster);
+  if (g_decode_variant == 1 && c.ok && workspace_bytes >= c.w_total && max_clusters_greedy_decode(c.smem, c.C) >= 1) {
+    __nv_bfloat16* whh_perm = reinterpret_cast<__nv_bfloat16*>(ws);
+    const int rows_l = c.C * 4 * c.up;
+    KLAUNCH(K_MISC, s, launch_permute_whh_cluster(static_cast<const __nv_bfloat16*>(W_hh), whh_perm, Hp, c.up, rows_l, s));
+    CUtensorMap tm_wj, tm_wl, tm_wp;
+    int rc;
+    if ((rc = make_map(&tm_wj, W, H, V, H, 64, 128))) return rc;
+    if ((rc = make_map(&tm_wl, whh_perm, Hp, rows_l, Hp, 64, 128))) return rc;
+    if ((rc = make_map(&tm_wp, W_proj, Hp, H, Hp, 64, 128))) return rc;
+    ClusterDecodeArgs a{};
+    a.B = B; a.Tmax = Tmax; a.V = V; a.H = H; a.Hp = Hp; a.blank = blank; a.S = max_symbols; a.sym_cap = sym_cap;
+    a.max_steps = Tmax * max_symbols + 1;
+    a.C = c.C; a.RJ = c.RJ; a.RP = c.RP; a.up = c.up; a.mtJ = c.mtJ; a.mtP = c.mtP; a.mtL = c.mtL; a.kbH = c.kbH; a.kbHp = c.kbHp;
+    a.n_stages = c.n_stages; a.tmem_cols = c.tmem_cols;
+    a.o_hj = c.o_hj; a.o_h0 = c.o_h0; a.o_h1 = c.o_h1; a.o_gates = c.o_gates; a.o_c = c.o_c; a.o_hown = c.o_hown;
+    a.o_amax = c.o_amax; a.o_part = c.o_part; a.o_state = c.o_state; a.o_bars = c.o_bars;
+    a.f = static_cast<const __nv_bfloat16*>(f); a.lens = lens; a.bias_j = bias; a.table = gate_table; a.bias_p = bias_proj;
+    a.sym = sym; a.n_sym = n_sym; a.prof = g_decode_prof;
+    cudaError_t e = cudaSuccess;
+    KLAUNCH(K_MISC, s, e = launch_greedy_decode_cluster(tm_wj, tm_wl, tm_wp, a, (B + 15) / 16, c.smem, s));
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(RNNT_ERR_CUDA, "greedy decode (cluster) launch -> %s", cudaGetErrorString(e)); }
+    CUDA_TRY(cudaGetLastError());
+    return RNNT_OK;
+  }
   const DecPlan d = make_dec_plan(B, V, H, Hp);
   if (!d.ok) return fail(RNNT_ERR_UNSUPPORTED, "fused greedy decode does not cover B=%d V=%d H=%d Hp=%d", B, V, H, Hp);
   if (workspace_bytes < d.w_total)
@@ -603,8 +686,6 @@ int rnnt_greedy_decode_lstm(const void* f, const int32_t* lens, const void* W, c
   if (G < d.nslJ || G < d.nslL || G < d.nslP)
     return fail(RNNT_ERR_UNSUPPORTED, "fused greedy decode needs %d co-resident CTAs, the device offers %d",
                 std::max(d.nslJ, std::max(d.nslL, d.nslP)), G);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
   CUDA_TRY(cudaMemsetAsync(ws, 0, d.w_whh, s));  // barrier counter, argmax keys, hj, both h buffers (h_0 = 0)
   __nv_bfloat16* whh_perm = reinterpret_cast<__nv_bfloat16*>(ws + d.w_whh);
   KLAUNCH(K_MISC, s, launch_permute_whh(static_cast<const __nv_bfloat16*>(W_hh), whh_perm, Hp, d.nu, d.nslL * d.nL, s));

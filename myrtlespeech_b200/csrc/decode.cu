@@ -48,11 +48,36 @@ __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long
   asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
   return v;
 }
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_addr(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ uint32_t ordered_bits(float x) {
   const uint32_t u = __float_as_uint(x);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Gate non-linearities of the cell: ex2.approx + rcp.approx (absolute error ~1e-7, far below the bf16 rounding of h);
+// the libm versions cost ~40 dependent instructions each on an epilogue warp that runs alone on its scheduler.
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return fmaf(2.0f, sigmoid_f(2.0f * x), -1.0f); }
 __device__ __forceinline__ float bf16_round_f(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 struct Pipe {
@@ -90,7 +115,7 @@ __device__ __forceinline__ void gemm_tile(Pipe& pp, const CUtensorMap* tm_a, int
       const uint32_t ph = (it / pp.n_stages) & 1;
       mbar_wait(&pp.full[s], ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {  // converged warp + elect.sync: no divergence waterfall around the tcgen05 instructions
         const uint32_t a_addr = smem_u32(pp.ring + s * kAStage);
         const uint32_t b_addr = w_smem + k * n * 128;
 #pragma unroll
@@ -227,9 +252,9 @@ greedy_decode_kernel(const __grid_constant__ CUtensorMap tm_hj, const __grid_con
                     const float af = __uint_as_float(raw[4 * jj + 1]) + __ldg(tb + p.Hp + u);
                     const float ag = __uint_as_float(raw[4 * jj + 2]) + __ldg(tb + 2 * p.Hp + u);
                     const float ao = __uint_as_float(raw[4 * jj + 3]) + __ldg(tb + 3 * p.Hp + u);
-                    const float c_new = sigmoid_f(af) * c_s[b * p.nu + ul] + sigmoid_f(ai) * tanhf(ag);
+                    const float c_new = sigmoid_f(af) * c_s[b * p.nu + ul] + sigmoid_f(ai) * tanh_f(ag);
                     c_s[b * p.nu + ul] = c_new;
-                    h_s[b * p.nu + ul] = __float2bfloat16_rn(sigmoid_f(ao) * tanhf(c_new));
+                    h_s[b * p.nu + ul] = __float2bfloat16_rn(sigmoid_f(ao) * tanh_f(c_new));
                   }
                 }
               }
@@ -397,6 +422,417 @@ __global__ void permute_whh_kernel(const __nv_bfloat16* __restrict__ W, __nv_bfl
   }
 }
 
+
+// ====================================================================================================================
+// Cluster variant (default): one thread-block cluster per 16 utterances, no grid-wide synchronisation at all.
+//
+// The three per-step products are turned around: the WEIGHTS are the M side of the MMA (128 output features per tile,
+// streamed from L2 by TMA -- they are static, so the producer warp runs ahead of the recurrence and the ring is always
+// full), the cluster's 16 utterances are the N side and their activations (h: 16 x Hp, hj: 16 x H, bf16) stay RESIDENT in
+// every CTA's shared memory.  CTA `rank` of a cluster of C owns 1/C of the rows of each weight matrix; after each
+// product it writes its slice of the new activation straight into the operand buffer (128-byte-swizzled K-major
+// layout, its slice is a contiguous run of 2 KB k-blocks) and pushes that run into the other C-1 CTAs with one
+// cp.async.bulk shared::cta -> shared::cluster each, completing on the RECEIVER's mbarrier; the per-utterance argmax is
+// exchanged the same way with st.async.  The MMA warp therefore waits only on transaction barriers, never on a
+// software barrier, and the W_hh . h product of step s+1 is issued while the argmax of step s is still in flight (it
+// does not depend on the emitted label -- only its epilogue does).
+// ====================================================================================================================
+__device__ unsigned long long g_dec_prof[16];  // cycles per epilogue stage, summed over steps (cluster 0, rank 0)
+#define DSTAMP(i)                                                \
+  do {                                                           \
+    if (prof) { const long long now_ = clock64(); acc[i] += now_ - last; last = now_; } \
+  } while (0)
+
+constexpr int kNB = 16;               // utterances per cluster == UMMA N
+constexpr int kKBlk = kNB * 128;      // bytes of one k-block of an activation buffer (16 rows x 128 B)
+constexpr int kMaxTiles = 10;         // accumulator tiles (L + P + J) per CTA
+constexpr int kTileCols = kNB;        // TMEM columns per accumulator tile.  (Spreading the four K = 16 MMAs of a k-block
+                                      // over four accumulators was measured: no change -- the ~110 cycles per MMA are
+                                      // not an accumulator dependency but the fixed cost of a tcgen05.mma at small N.)
+
+// This thread's TMEM lane of one accumulator tile: v[n], n = utterance.
+__device__ __forceinline__ void ld_tile_sum(uint32_t taddr, float (&v)[kNB]) {
+  uint32_t a[kNB];
+  tmem_ld16(taddr, a);
+  tmem_ld_wait();
+#pragma unroll
+  for (int n = 0; n < kNB; ++n) v[n] = __uint_as_float(a[n]);
+}
+
+__device__ __forceinline__ uint32_t act_offset(int n, int utt) {  // byte offset of element (utt, feature n), SW128 K-major
+  return static_cast<uint32_t>((n >> 6) * kKBlk + utt * 128 + ((((n & 63) >> 3) ^ (utt & 7)) << 4) + (n & 7) * 2);
+}
+
+__global__ void __launch_bounds__(kDecThreads, 1)
+greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __grid_constant__ CUtensorMap tm_wl,
+                             const __grid_constant__ CUtensorMap tm_wp, const ClusterDecodeArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* hj = smem + p.o_hj;
+  uint8_t* hb[2] = {smem + p.o_h0, smem + p.o_h1};
+  float* gates = reinterpret_cast<float*>(smem + p.o_gates);                 // [4][32][16]
+  float* c_s = reinterpret_cast<float*>(smem + p.o_c);                       // [up][16]
+  __nv_bfloat16* hown = reinterpret_cast<__nv_bfloat16*>(smem + p.o_hown);   // [up][16]
+  unsigned long long* amax_s = reinterpret_cast<unsigned long long*>(smem + p.o_amax);  // [C][16]
+  unsigned long long* part = reinterpret_cast<unsigned long long*>(smem + p.o_part);    // [4][16]
+  int* s_t = reinterpret_cast<int*>(smem + p.o_state);
+  int* s_em = s_t + kNB;
+  int* s_n = s_em + kNB;
+  int* s_lab = s_n + kNB;
+  int* s_len = s_lab + kNB;
+  volatile int* s_go = s_len + kNB;  // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.o_bars);
+  uint64_t* full_bar = bars;                          // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [kMaxTiles]
+  uint64_t* hfull_bar = tfull_bar + kMaxTiles;        // [2]
+  uint64_t* hjfull_bar = hfull_bar + 2;
+  uint64_t* amaxfull_bar = hjfull_bar + 1;
+  uint64_t* step_bar = amaxfull_bar + 1;
+  uint64_t* fin_bar = step_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fin_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int C = p.C;
+  const int b0 = (blockIdx.x / C) * kNB;
+  const int n_h_bytes = (C * p.up / 64) * kKBlk;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tm_wj); prefetch_tmap(&tm_wl); prefetch_tmap(&tm_wp);
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kMaxTiles; ++i) mbar_init(&tfull_bar[i], 1);
+    mbar_init(&hfull_bar[0], 1); mbar_init(&hfull_bar[1], 1);
+    mbar_init(hjfull_bar, 1); mbar_init(amaxfull_bar, 1); mbar_init(step_bar, 1); mbar_init(fin_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < n_h_bytes / 4; i += kDecThreads) {
+    reinterpret_cast<uint32_t*>(hb[0])[i] = 0u;   // h_{-1} = 0
+    reinterpret_cast<uint32_t*>(hb[1])[i] = 0u;
+  }
+  for (int i = threadIdx.x; i < p.up * kNB; i += kDecThreads) { c_s[i] = 0.0f; hown[i] = __float2bfloat16(0.0f); }
+  if (threadIdx.x < kNB) {
+    const int b = b0 + threadIdx.x;
+    s_t[threadIdx.x] = 0; s_em[threadIdx.x] = 0; s_n[threadIdx.x] = 0;
+    s_len[threadIdx.x] = b < p.B ? p.lens[b] : 0;
+    s_lab[threadIdx.x] = b < p.B ? p.V : -1;  // start of sequence: every utterance steps the LSTM once
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers and buffers exist before anybody pushes into them
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int slotP0 = p.mtL, slotJ0 = p.mtL + p.mtP;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ weight stream (runs ahead of the recurrence)
+    if (lane == 0) {
+      uint32_t it = 0;
+      const bool prof = p.prof && blockIdx.x == 0;
+      long long w_empty = 0, w_step = 0;
+      auto push = [&](const CUtensorMap* tm, int row0, int kb) {
+        for (int k = 0; k < kb; ++k, ++it) {
+          const int st = it % p.n_stages;
+          const long long t0 = prof ? clock64() : 0;
+          mbar_wait(&empty_bar[st], ((it / p.n_stages) & 1) ^ 1);
+          if (prof) w_empty += clock64() - t0;
+          mbar_arrive_expect_tx(&full_bar[st], kAStage);
+          tma_load_2d(ring + st * kAStage, tm, &full_bar[st], k * kBK, row0);
+        }
+      };
+      for (int s = 0; s <= p.max_steps; ++s) {
+        for (int m = 0; m < p.mtL; ++m) push(&tm_wl, static_cast<int>(rank) * 4 * p.up + m * kBM, p.kbHp);
+        const long long t0 = prof ? clock64() : 0;
+        if (s > 0) { mbar_wait(step_bar, (s - 1) & 1); if (!s_go[(s - 1) & 1]) break; }
+        if (prof) w_step += clock64() - t0;
+        for (int m = 0; m < p.mtP; ++m) push(&tm_wp, static_cast<int>(rank) * p.RP + m * kBM, p.kbHp);
+        for (int m = 0; m < p.mtJ; ++m) push(&tm_wj, static_cast<int>(rank) * p.RJ + m * kBM, p.kbH);
+      }
+      if (prof) { g_dec_prof[10] = w_empty; g_dec_prof[11] = w_step; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issue
+    // Converged warp, elect.sync-predicated tcgen05 instructions, running descriptors and a poll-ahead try_wait: under
+    // `if (lane == 0)` ptxas wraps every UTCHMMA in a divergence waterfall that costs ~160 cycles per MMA, 20x the 8
+    // cycles the tensor core needs for a 128 x 16 x 16 product (DESIGN.md finding 2).
+    const uint32_t idesc = make_idesc_bf16(kBM, kNB, false, false);
+    const bool prof = p.prof && blockIdx.x == 0 && lane == 0;
+    long long w_full = 0, w_dep = 0;
+    const uint64_t ad0 = make_smem_desc_sw128(smem_u32(ring), 16, 1024);
+    const uint32_t fb0 = smem_u32(&full_bar[0]), eb0 = smem_u32(&empty_bar[0]);
+    int st = 0;
+    uint32_t ph = 0, fb = fb0, eb = eb0;
+    uint64_t ad = ad0;
+    bool ready = false;
+    auto tile = [&](uint32_t b_base, int kb, int slot) {
+      const uint64_t bd0 = make_smem_desc_sw128(b_base, 16, 1024);
+      const uint32_t d_tmem = tmem + slot * kTileCols, tf = smem_u32(&tfull_bar[slot]);
+      for (int k = 0; k < kb; ++k) {
+        if (!ready) {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_wait_addr(fb, ph);
+          if (prof) w_full += clock64() - t0;
+        }
+        tc_fence_after();
+        const uint64_t bd = bd0 + static_cast<uint64_t>(k) * (kKBlk >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk) umma_bf16(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+          umma_commit_addr(eb);
+          if (k == kb - 1) umma_commit_addr(tf);
+        }
+        __syncwarp();
+        if (++st == p.n_stages) { st = 0; ph ^= 1; ad = ad0; fb = fb0; eb = eb0; }
+        else { ad += kAStage >> 4; fb += 8; eb += 8; }
+        ready = mbar_try_wait_addr(fb, ph);
+      }
+    };
+    for (int s = 0; s <= p.max_steps; ++s) {
+      const int cur = s & 1, nxt = cur ^ 1;
+      for (int m = 0; m < p.mtL; ++m) tile(smem_u32(hb[cur]), p.kbHp, m);   // speculative for s > 0: needs no label
+      long long t0 = prof ? clock64() : 0;
+      if (s > 0) { mbar_wait(step_bar, (s - 1) & 1); if (!s_go[(s - 1) & 1]) break; }
+      mbar_wait(&hfull_bar[nxt], (s >> 1) & 1);
+      if (prof) w_dep += clock64() - t0;
+      tc_fence_after();
+      for (int m = 0; m < p.mtP; ++m) tile(smem_u32(hb[nxt]), p.kbHp, slotP0 + m);
+      t0 = prof ? clock64() : 0;
+      mbar_wait(hjfull_bar, s & 1);
+      if (prof) w_dep += clock64() - t0;
+      tc_fence_after();
+      for (int m = 0; m < p.mtJ; ++m) tile(smem_u32(hj), p.kbH, slotJ0 + m);
+    }
+    if (prof) { g_dec_prof[12] = w_full; g_dec_prof[13] = w_dep; }
+    if (elect_one()) umma_commit(fin_bar);
+    __syncwarp();
+    mbar_wait(fin_bar, 0);
+    tc_fence_after();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;            // TMEM lane == weight row inside the tile
+    const int et = (warp - 2) * 32 + lane;       // 0..127
+    const uint32_t lane_taddr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    const size_t gate_pitch = static_cast<size_t>(4) * p.Hp;
+    const uint32_t slice_h = static_cast<uint32_t>(p.up / 64) * kKBlk;
+    const uint32_t slice_p = static_cast<uint32_t>(p.RP / 64) * kKBlk;
+
+    const bool prof = p.prof && blockIdx.x == 0 && et == 0;
+    long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long last = clock64();
+    int n_steps = 0;
+    for (int s = 0; s <= p.max_steps; ++s) {
+      const int cur = s & 1, nxt = cur ^ 1;
+      const uint32_t par = s & 1;
+      ++n_steps;
+      // ---------------------------------------------------------------- L: gates -> cell -> h
+      for (int m = 0; m < p.mtL; ++m) {
+        const int u = static_cast<int>(rank) * p.up + m * 32 + lane;   // this thread: gate `quad` of unit u
+        float tv[kNB];
+#pragma unroll
+        for (int n = 0; n < kNB; ++n) {
+          const int lab = s_lab[n];
+          tv[n] = (lab >= 0 && u < p.Hp) ? __ldg(p.table + static_cast<size_t>(lab) * gate_pitch + quad * p.Hp + u) : 0.0f;
+        }
+        if (m == 0) DSTAMP(0);   // table gather issued
+        mbar_wait(&tfull_bar[m], par);
+        if (m == 0) DSTAMP(1);   // waited for the L accumulator
+        tc_fence_after();
+        float acc_v[kNB];
+        ld_tile_sum(lane_taddr + m * kTileCols, acc_v);
+        float4* gdst = reinterpret_cast<float4*>(gates + (quad * 32 + lane) * kNB);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float a[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = acc_v[4 * q + e] + tv[4 * q + e];
+            a[e] = quad == 2 ? tanh_f(x) : sigmoid_f(x);
+          }
+          gdst[q] = make_float4(a[0], a[1], a[2], a[3]);
+        }
+        tc_fence_before();
+        named_bar_sync(1, 128);
+        {
+          const int j = et >> 2, ul = m * 32 + j, n_feat = static_cast<int>(rank) * p.up + ul;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = (et & 3) * 4 + q;
+            __nv_bfloat16 hv;
+            if (s_lab[n] >= 0) {
+              const float gi = gates[(0 * 32 + j) * kNB + n], gf = gates[(1 * 32 + j) * kNB + n];
+              const float gg = gates[(2 * 32 + j) * kNB + n], go = gates[(3 * 32 + j) * kNB + n];
+              const float c_new = gf * c_s[ul * kNB + n] + gi * gg;
+              c_s[ul * kNB + n] = c_new;
+              hv = __float2bfloat16_rn(go * tanh_f(c_new));
+              hown[ul * kNB + n] = hv;
+            } else {
+              hv = hown[ul * kNB + n];
+            }
+            if (n_feat >= p.Hp) hv = __float2bfloat16(0.0f);
+            *reinterpret_cast<__nv_bfloat16*>(hb[nxt] + act_offset(n_feat, n)) = hv;
+          }
+        }
+        named_bar_sync(1, 128);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (et == 0) {
+        mbar_arrive_expect_tx(&hfull_bar[nxt], static_cast<uint32_t>(C - 1) * slice_h);
+        const uint32_t src = smem_u32(hb[nxt]) + rank * slice_h, bar = smem_u32(&hfull_bar[nxt]);
+        for (int d = 1; d < C; ++d) {
+          const uint32_t dst = (rank + d) % C;
+          bulk_copy_to_cluster(mapa_u32(src, dst), src, slice_h, mapa_u32(bar, dst));
+        }
+      }
+      DSTAMP(2);  // L epilogue + push issued
+      // ---------------------------------------------------------------- P: g -> hj = tanh(f + g)
+      for (int m = 0; m < p.mtP; ++m) {
+        const int lr = m * kBM + row, n_feat = static_cast<int>(rank) * p.RP + lr;
+        const bool mine = lr < p.RP, valid = mine && n_feat < p.H;
+        float fv[kNB];
+#pragma unroll
+        for (int n = 0; n < kNB; ++n) {
+          const int b = b0 + n;
+          int t = s_t[n];
+          t = t < p.Tmax ? t : p.Tmax - 1;
+          fv[n] = (valid && b < p.B)
+                      ? __bfloat162float(__ldg(p.f + (static_cast<size_t>(b) * p.Tmax + t) * p.H + n_feat)) : 0.0f;
+        }
+        const float bp = (valid && p.bias_p) ? __ldg(p.bias_p + n_feat) : 0.0f;
+        mbar_wait(&tfull_bar[slotP0 + m], par);
+        if (m == p.mtP - 1) DSTAMP(3);  // waited for the P accumulator (h exchange + P product)
+        tc_fence_after();
+        float acc_v[kNB];
+        ld_tile_sum(lane_taddr + (slotP0 + m) * kTileCols, acc_v);
+        if (mine) {
+#pragma unroll
+          for (int n = 0; n < kNB; ++n) {
+            const float g = bf16_round_f(acc_v[n] + bp);
+            const float hv = valid ? tanh_approx(fv[n] + g) : 0.0f;
+            *reinterpret_cast<__nv_bfloat16*>(hj + act_offset(n_feat, n)) = __float2bfloat16_rn(hv);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (et == 0) {
+        mbar_arrive_expect_tx(hjfull_bar, static_cast<uint32_t>(C - 1) * slice_p);
+        const uint32_t src = smem_u32(hj) + rank * slice_p, bar = smem_u32(hjfull_bar);
+        for (int d = 1; d < C; ++d) {
+          const uint32_t dst = (rank + d) % C;
+          bulk_copy_to_cluster(mapa_u32(src, dst), src, slice_p, mapa_u32(bar, dst));
+        }
+      }
+      DSTAMP(4);  // P epilogue + push issued
+      // ---------------------------------------------------------------- J: logits -> argmax
+      unsigned long long best = 0ull;  // lane n < 16 keeps the best key of utterance n over this warp's rows
+      for (int m = 0; m < p.mtJ; ++m) {
+        const int lr = m * kBM + row, v = static_cast<int>(rank) * p.RJ + lr;
+        const bool valid = lr < p.RJ && v < p.V;
+        const float bj = (valid && p.bias_j) ? __ldg(p.bias_j + v) : 0.0f;
+        mbar_wait(&tfull_bar[slotJ0 + m], par);
+        if (m == p.mtJ - 1) DSTAMP(5);  // waited for the J accumulator (hj exchange + J product)
+        tc_fence_after();
+        float acc_v[kNB];
+        ld_tile_sum(lane_taddr + (slotJ0 + m) * kTileCols, acc_v);
+#pragma unroll
+        for (int n = 0; n < kNB; ++n) {
+          const float z = acc_v[n] + bj;
+          const uint32_t ob = (valid && z == z) ? ordered_bits(z) : 0u;
+          const uint32_t mx = __reduce_max_sync(0xffffffffu, ob);
+          const uint32_t mv = __reduce_min_sync(0xffffffffu, (ob == mx && ob != 0u) ? static_cast<uint32_t>(v) : 0xFFFFFFFFu);
+          const unsigned long long key = mx ? ((static_cast<unsigned long long>(mx) << 32) | (0xFFFFFFFFu - mv)) : 0ull;
+          if (lane == n && key > best) best = key;
+        }
+      }
+      if (lane < kNB) part[quad * kNB + lane] = best;
+      tc_fence_before();
+      named_bar_sync(1, 128);
+      if (et < kNB) {
+        unsigned long long key = part[et];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) { const unsigned long long o = part[q * kNB + et]; key = o > key ? o : key; }
+        const uint32_t slot = smem_u32(amax_s + rank * kNB + et), bar = smem_u32(amaxfull_bar);
+        for (int d = 0; d < C; ++d) st_async_u64(mapa_u32(slot, d), key, mapa_u32(bar, d));
+      }
+      if (et == 0) mbar_arrive_expect_tx(amaxfull_bar, static_cast<uint32_t>(C) * kNB * 8);
+      DSTAMP(6);  // J epilogue + keys sent
+      mbar_wait(amaxfull_bar, par);
+      DSTAMP(7);  // waited for everybody's keys
+      // ---------------------------------------------------------------- bookkeeping (replicated in every CTA)
+      if (warp == 2) {
+        int active = 0;
+        if (lane < kNB) {
+          unsigned long long key = 0ull;
+          for (int r = 0; r < C; ++r) { const unsigned long long o = amax_s[r * kNB + lane]; key = o > key ? o : key; }
+          int t = s_t[lane], lab = -1;
+          if (t < s_len[lane]) {
+            const int k = key ? static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key)) : p.blank;
+            int em = s_em[lane];
+            if (k != p.blank) {
+              const int n = s_n[lane];
+              if (rank == 0 && n < p.sym_cap) p.sym[static_cast<size_t>(b0 + lane) * p.sym_cap + n] = k;
+              s_n[lane] = n + 1;
+              ++em;
+              lab = k;
+            }
+            if (lab < 0 || em >= p.S) { ++t; em = 0; }
+            s_t[lane] = t; s_em[lane] = em;
+          }
+          s_lab[lane] = lab;
+          active = t < s_len[lane] ? 1 : 0;
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, active);
+        if (lane == 0) s_go[par] = any != 0u;
+      }
+      named_bar_sync(1, 128);
+      if (et == 0) mbar_arrive(step_bar);
+      DSTAMP(8);  // bookkeeping
+      if (!s_go[par]) break;
+    }
+    if (prof) {
+      for (int i = 0; i < 9; ++i) g_dec_prof[i] = static_cast<unsigned long long>(acc[i]);
+      g_dec_prof[9] = static_cast<unsigned long long>(n_steps);
+    }
+    if (rank == 0 && et < kNB && b0 + et < p.B) p.n_sym[b0 + et] = s_n[et] < p.sym_cap ? s_n[et] : p.sym_cap;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while a peer could still address its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, p.tmem_cols);
+  }
+}
+
+// W_hh [4 Hp][Hp] (torch gate order) -> rows [rank][tile m][gate][32 units]: CTA `rank` owns units
+// [rank*up, rank*up + up), one 128-row tile carries the four gates of 32 units, one gate per TMEM lane quadrant.
+__global__ void permute_whh_cluster_kernel(const __nv_bfloat16* __restrict__ W, __nv_bfloat16* __restrict__ out, int Hp,
+                                           int up, int n_rows) {
+  const int R = blockIdx.x;
+  if (R >= n_rows) return;
+  const int per_rank = 4 * up;
+  const int rank = R / per_rank, rem = R - rank * per_rank;
+  const int m = rem >> 7, gate = (rem >> 5) & 3, j = rem & 31;
+  const int u = rank * up + m * 32 + j;
+  __nv_bfloat16* dst = out + static_cast<size_t>(R) * Hp;
+  if (u < Hp) {
+    const __nv_bfloat16* src = W + (static_cast<size_t>(gate) * Hp + u) * Hp;
+    for (int i = threadIdx.x; i < Hp; i += blockDim.x) dst[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < Hp; i += blockDim.x) dst[i] = __float2bfloat16(0.0f);
+  }
+}
+
 namespace {
 bool g_decode_cooperative = true;
 }
@@ -437,6 +873,55 @@ cudaError_t launch_greedy_decode(const CUtensorMap& tm_hj, const CUtensorMap& tm
   cfg.attrs = attr;
   cfg.numAttrs = g_decode_cooperative ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, greedy_decode_kernel, tm_hj, tm_hbuf, tm_wj, tm_wl, tm_wp, a);
+}
+
+
+void launch_permute_whh_cluster(const __nv_bfloat16* W, __nv_bfloat16* out, int Hp, int up, int n_rows, cudaStream_t s) {
+  permute_whh_cluster_kernel<<<n_rows, 128, 0, s>>>(W, out, Hp, up, n_rows);
+}
+
+int read_decode_prof(unsigned long long* out, int n) {
+  if (n > 16) n = 16;
+  return cudaMemcpyFromSymbol(out, g_dec_prof, sizeof(unsigned long long) * n) == cudaSuccess ? n : -1;
+}
+
+int max_clusters_greedy_decode(int smem_bytes, int C) {
+  if (cudaFuncSetAttribute(greedy_decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  if (C > 8) cudaFuncSetAttribute(greedy_decode_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(C);
+  cfg.blockDim = dim3(kDecThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, greedy_decode_cluster_kernel, &cfg) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+cudaError_t launch_greedy_decode_cluster(const CUtensorMap& tm_wj, const CUtensorMap& tm_wl, const CUtensorMap& tm_wp,
+                                         const ClusterDecodeArgs& a, int n_clusters, int smem_bytes, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(greedy_decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  if (a.C > 8) cudaFuncSetAttribute(greedy_decode_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_clusters * a.C);
+  cfg.blockDim = dim3(kDecThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = a.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, greedy_decode_cluster_kernel, tm_wj, tm_wl, tm_wp, a);
 }
 
 }  // namespace rnnt

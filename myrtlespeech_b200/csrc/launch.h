@@ -184,6 +184,31 @@ cudaError_t launch_greedy_decode(const CUtensorMap& tm_hj, const CUtensorMap& tm
                                  int smem_bytes, cudaStream_t s);
 void set_decode_cooperative(int v);
 
+// Cluster variant: one thread-block cluster per 16 utterances, activations resident, weights streamed (see decode.cu).
+struct ClusterDecodeArgs {
+  int B, Tmax, V, H, Hp, blank, S, sym_cap, max_steps;
+  int C;                   // CTAs per cluster
+  int RJ, RP, up;          // per-CTA vocabulary rows, projection rows, hidden units (multiples of 64)
+  int mtJ, mtP, mtL;       // 128-row accumulator tiles per CTA and product
+  int kbH, kbHp;           // k-blocks over H / Hp
+  int n_stages, tmem_cols;
+  int o_hj, o_h0, o_h1, o_gates, o_c, o_hown, o_amax, o_part, o_state, o_bars;
+  const __nv_bfloat16* f;
+  const int* lens;
+  const float* bias_j;
+  const float* table;
+  const float* bias_p;
+  int* sym;
+  int* n_sym;
+  int prof;                // != 0: cluster 0 / rank 0 sums clock64 cycles per epilogue stage into g_dec_prof
+};
+int read_decode_prof(unsigned long long* out, int n);
+void launch_permute_whh_cluster(const __nv_bfloat16* W, __nv_bfloat16* out, int Hp, int up, int n_rows, cudaStream_t s);
+int max_clusters_greedy_decode(int smem_bytes, int C);
+cudaError_t launch_greedy_decode_cluster(const CUtensorMap& tm_wj, const CUtensorMap& tm_wl, const CUtensorMap& tm_wp,
+                                         const ClusterDecodeArgs& a, int n_clusters, int smem_bytes, cudaStream_t s);
+
+
 void set_gemm_dbg(int v);
 int read_gemm_prof(unsigned long long* out, int n);
 int smem_bytes_fwd(int nc_total);

@@ -20,8 +20,10 @@ dec = RNNTGreedyDecoder(V - 1, model, max_symbols_per_step=S)
 f = torch.randn(B, T, H, device="cuda").bfloat16()
 lens = torch.full((B,), T, dtype=torch.int32)
 outs = {}
-for fused in (True, False):
-    dec.USE_FUSED_LOOP = fused
+from myrtlespeech_b200 import _lib
+for fused in ("cluster", "gridsync", False):
+    dec.USE_FUSED_LOOP = bool(fused)
+    _lib.load().rnnt_debug_set(b"decode_variant", 1 if fused == "cluster" else 0)
     for it in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); t0 = time.perf_counter(); e0.record()
@@ -29,9 +31,11 @@ for fused in (True, False):
         e1.record(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
         n_sym = sum(len(o) for o in out)
         steps = max(len(o) for o in out) + T
-        print(f"{'one-launch' if fused else 'graph-step'} pass {it}: wall {dt*1e3:.1f} ms (device {e0.elapsed_time(e1):.1f} ms), "
+        print(f"{('one-launch/' + fused) if fused else 'graph-step'} pass {it}: wall {dt*1e3:.1f} ms (device {e0.elapsed_time(e1):.1f} ms), "
               f"{B/dt:.1f} utt/s, {n_sym} symbols ({n_sym/B/T:.2f} per frame), <= {steps} steps "
               f"-> {e0.elapsed_time(e1)*1e3/steps:.1f} us/step", flush=True)
     outs[fused] = out
-same = sum(a == b for a, b in zip(outs[True], outs[False]))
-print(f"transcripts identical between the two paths (bf16 LSTM vs cuDNN fp32 LSTM): {same}/{B}")
+same = sum(a == b for a, b in zip(outs["cluster"], outs["gridsync"]))
+print(f"transcripts identical between the two one-launch schedules: {same}/{B}")
+same = sum(a == b for a, b in zip(outs["cluster"], outs[False]))
+print(f"transcripts identical between one-launch (bf16 LSTM operands) and graph-step (cuDNN fp32 LSTM): {same}/{B}")

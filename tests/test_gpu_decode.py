@@ -136,8 +136,18 @@ LSTM_CASES = [
 ]
 
 
+@pytest.fixture(params=[1, 0], ids=["cluster", "gridsync"])
+def decode_variant(request):
+    """Both schedules of the one-launch decode: 1 = one thread-block cluster per 16 utterances (default),
+    0 = N-split over the whole grid with grid barriers."""
+    from myrtlespeech_b200 import _lib
+    _lib.load().rnnt_debug_set(b"decode_variant", request.param)
+    yield request.param
+    _lib.load().rnnt_debug_set(b"decode_variant", 1)
+
+
 @pytest.mark.parametrize("seed,B,T,V,H,Hp,E,S", LSTM_CASES)
-def test_fused_lstm_decode_matches_oracle(seed, B, T, V, H, Hp, E, S):
+def test_fused_lstm_decode_matches_oracle(decode_variant, seed, B, T, V, H, Hp, E, S):
     joint, pred, f, lens = _lstm_case(seed, B, T, V, H, Hp, E)
     blank = V - 1
     want, margins = _oracle_transcripts(joint, pred, f, lens, blank, S)
@@ -160,7 +170,7 @@ def test_fused_lstm_decode_matches_oracle(seed, B, T, V, H, Hp, E, S):
     assert all(len(g) <= int(l) * S for g, l in zip(got, lens))
 
 
-def test_fused_lstm_decode_is_deterministic_and_handles_empty_batch_rows():
+def test_fused_lstm_decode_is_deterministic_and_handles_empty_batch_rows(decode_variant):
     joint, pred, f, _ = _lstm_case(3, 6, 11, 40, 64, 64, 32)
     lens = torch.tensor([11, 0, 5, 0, 1, 11], dtype=torch.int32)
     model = RNNT(torch.nn.Identity(), pred, joint).cuda()
