@@ -145,6 +145,37 @@ def run_reference(args, B, T, U, V, H, desc, rank):
     print(json.dumps(out), flush=True)
 
 
+def decode_bench(dev):
+    """BASELINE.json configs[4]: greedy decode, B=128 T=500 V=H=1024, max 4 symbols per frame, through the public
+    RNNTGreedyDecoder (host f in pinned memory -> device, transcripts back as List[List[int]]).  Random-init single-layer
+    LSTM prediction network (E=256, Hp=512); measured after the training-step timing, not part of `value`."""
+    import torch
+    from myrtlespeech_b200.model import RNNTJoint
+    from myrtlespeech_b200.model.rnn_t import RNNT, RNNTPredictionNet
+    from myrtlespeech_b200.post_process import RNNTGreedyDecoder
+    B, T, V, H, S = 128, 500, 1024, 1024, 4
+    g = torch.Generator().manual_seed(7)
+    torch.manual_seed(7)
+    model = RNNT(torch.nn.Identity(), RNNTPredictionNet(V, 256, 512, 1, H), RNNTJoint(H, V)).to(dev)
+    dec = RNNTGreedyDecoder(V - 1, model, max_symbols_per_step=S)
+    f_host = torch.randn(B, T, H, generator=g).bfloat16().pin_memory()
+    lens = torch.full((B,), T, dtype=torch.int32)
+    best, n_sym = None, 0
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = dec(f_host.to(dev, non_blocking=True), lens)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+        n_sym = sum(len(o) for o in out)
+    return {"workload": "configs[4]: greedy decode B=128 T=500 V=1024 H=1024 max_symbols_per_step=4, LSTM prediction net "
+                        "E=256 Hp=512 (random init)", "ms_per_batch": round(best * 1e3, 2),
+            "utterances_per_s": round(B / best, 1), "symbols_emitted": n_sym, "decode_steps": int(n_sym / B) + T,
+            "kernel": "greedy_decode_cluster_kernel (one launch per batch)", "timing": "host wall clock around "
+            "RNNTGreedyDecoder.forward incl. the H2D copy of f and the D2H copy of the transcripts, best of 3"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +184,7 @@ def main():
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the configs[4] greedy-decode measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -348,6 +380,13 @@ def main():
             cpu = {"value": round(r["utt_per_s"], 4), "unit": "utterances/s", "cores": r["cores"], "kind": "port",
                    "sample": r["sample"]}
 
+        decode = None
+        if world == 1 and not args.no_decode:
+            try:
+                decode = decode_bench(dev)
+            except Exception as e:  # the decode figure is an extra; never lose the headline line over it
+                decode = {"error": repr(e)}
+
         h2d = f.numel() * 2 + g.numel() * 2 + y.numel() * 4
         out = {
             "metric": METRIC, "value": round(B * world * args.steps / (ms_total * 1e-3), 2), "unit": "utterances/s",
@@ -371,6 +410,7 @@ def main():
             "kernels": kernels,
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "decode": decode,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
