@@ -300,13 +300,13 @@ CDecPlan make_cdec_plan(int B, int V, int H, int Hp, int C) {
   if (d.mtL + d.mtP + d.mtJ > 10) return d;
   d.kbH = (H + 63) / 64; d.kbHp = (Hp + 63) / 64;
   d.tmem_cols = 32;
-  while (d.tmem_cols < 16 * (d.mtL + d.mtP + d.mtJ)) d.tmem_cols *= 2;
+  while (d.tmem_cols < 32 * (d.mtL + d.mtP + d.mtJ)) d.tmem_cols *= 2;   // two partial accumulators x 16 utterances per tile
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return static_cast<int>(r); };
   d.o_hj = take(static_cast<size_t>(C) * d.RP / 64 * 2048);
   d.o_h0 = take(static_cast<size_t>(C) * d.up / 64 * 2048);
   d.o_h1 = take(static_cast<size_t>(C) * d.up / 64 * 2048);
-  d.o_gates = take(4 * 32 * 16 * sizeof(float));
+  d.o_gates = take(static_cast<size_t>(d.mtL) * 4 * 32 * 16 * sizeof(float));
   d.o_c = take(static_cast<size_t>(d.up) * 16 * sizeof(float));
   d.o_hown = take(static_cast<size_t>(d.up) * 16 * 2);
   d.o_amax = take(static_cast<size_t>(C) * 16 * 8);
@@ -316,7 +316,7 @@ CDecPlan make_cdec_plan(int B, int V, int H, int Hp, int C) {
   const size_t fixed = o + 1024, cap = 227 * 1024;
   if (fixed + 3 * 16384 > cap) return d;
   d.n_stages = static_cast<int>((cap - fixed) / 16384);
-  if (d.n_stages > 8) d.n_stages = 8;
+  if (d.n_stages > 12) d.n_stages = 12;
   const int ring = d.n_stages * 16384;
   d.o_hj += ring; d.o_h0 += ring; d.o_h1 += ring; d.o_gates += ring; d.o_c += ring; d.o_hown += ring; d.o_amax += ring;
   d.o_part += ring; d.o_state += ring; d.o_bars += ring;

@@ -32,7 +32,7 @@ constexpr int kBK = 64;               // bf16 per k-block (one 128-byte swizzle 
 constexpr int kAStage = kBM * kBK * 2;  // 16 KB
 constexpr int kDecThreads = 192;      // warp 0: TMA, warp 1: MMA issue, warps 2..5: epilogue
 constexpr int kDecTmemCols = 256;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 
 __device__ __forceinline__ void fence_proxy_async_global_() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* ptr) {
@@ -444,26 +444,32 @@ __device__ unsigned long long g_dec_prof[16];  // cycles per epilogue stage, sum
   } while (0)
 
 constexpr int kNB = 16;               // utterances per cluster == UMMA N
+constexpr int kNH = kNB / 2;           // utterances per epilogue warp
 constexpr int kKBlk = kNB * 128;      // bytes of one k-block of an activation buffer (16 rows x 128 B)
+constexpr int kCThreads = 352;        // warp 0: TMA, warps 1 and 10: MMA issue, warps 2..9: epilogue
+constexpr int kMma2Warp = 10;
+constexpr int kEpiThreads = 256;
 constexpr int kMaxTiles = 10;         // accumulator tiles (L + P + J) per CTA
-constexpr int kTileCols = kNB;        // TMEM columns per accumulator tile.  (Spreading the four K = 16 MMAs of a k-block
-                                      // over four accumulators was measured: no change -- the ~110 cycles per MMA are
-                                      // not an accumulator dependency but the fixed cost of a tcgen05.mma at small N.)
+constexpr int kTileCols = 2 * kNB;    // TMEM columns per accumulator tile: one partial accumulator per issuing warp.
+                                      // (Spreading one warp's MMAs over four accumulators was measured: no change --
+                                      // the cost per MMA is issue latency of the thread, not an accumulator dependency.)
 
-// This thread's TMEM lane of one accumulator tile: v[n], n = utterance.
-__device__ __forceinline__ void ld_tile_sum(uint32_t taddr, float (&v)[kNB]) {
-  uint32_t a[kNB];
-  tmem_ld16(taddr, a);
+// This thread's 8 utterances of one accumulator tile: the sum of the two issuing warps' partial accumulators (the
+// second one was never written when the product has a single k-block).
+__device__ __forceinline__ void ld_acc(uint32_t taddr, bool two, float (&v)[kNH]) {
+  uint32_t a[kNH], b[kNH];
+  tmem_ld8(taddr, a);
+  tmem_ld8(taddr + kNB, b);
   tmem_ld_wait();
 #pragma unroll
-  for (int n = 0; n < kNB; ++n) v[n] = __uint_as_float(a[n]);
+  for (int i = 0; i < kNH; ++i) v[i] = two ? __uint_as_float(a[i]) + __uint_as_float(b[i]) : __uint_as_float(a[i]);
 }
 
 __device__ __forceinline__ uint32_t act_offset(int n, int utt) {  // byte offset of element (utt, feature n), SW128 K-major
   return static_cast<uint32_t>((n >> 6) * kKBlk + utt * 128 + ((((n & 63) >> 3) ^ (utt & 7)) << 4) + (n & 7) * 2);
 }
 
-__global__ void __launch_bounds__(kDecThreads, 1)
+__global__ void __launch_bounds__(kCThreads, 1)
 greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __grid_constant__ CUtensorMap tm_wl,
                              const __grid_constant__ CUtensorMap tm_wp, const ClusterDecodeArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -471,7 +477,7 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
   uint8_t* ring = smem;
   uint8_t* hj = smem + p.o_hj;
   uint8_t* hb[2] = {smem + p.o_h0, smem + p.o_h1};
-  float* gates = reinterpret_cast<float*>(smem + p.o_gates);                 // [4][32][16]
+  float* gates = reinterpret_cast<float*>(smem + p.o_gates);                 // [mtL][4][32][16]
   float* c_s = reinterpret_cast<float*>(smem + p.o_c);                       // [up][16]
   __nv_bfloat16* hown = reinterpret_cast<__nv_bfloat16*>(smem + p.o_hown);   // [up][16]
   unsigned long long* amax_s = reinterpret_cast<unsigned long long*>(smem + p.o_amax);  // [C][16]
@@ -502,20 +508,20 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_wj); prefetch_tmap(&tm_wl); prefetch_tmap(&tm_wp);
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < kMaxTiles; ++i) mbar_init(&tfull_bar[i], 1);
+    for (int i = 0; i < kMaxTiles; ++i) mbar_init(&tfull_bar[i], 2);   // one arrival per issuing warp
     mbar_init(&hfull_bar[0], 1); mbar_init(&hfull_bar[1], 1);
-    mbar_init(hjfull_bar, 1); mbar_init(amaxfull_bar, 1); mbar_init(step_bar, 1); mbar_init(fin_bar, 1);
+    mbar_init(hjfull_bar, 1); mbar_init(amaxfull_bar, 1); mbar_init(step_bar, 1); mbar_init(fin_bar, 2);
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < n_h_bytes / 4; i += kDecThreads) {
+  for (int i = threadIdx.x; i < n_h_bytes / 4; i += kCThreads) {
     reinterpret_cast<uint32_t*>(hb[0])[i] = 0u;   // h_{-1} = 0
     reinterpret_cast<uint32_t*>(hb[1])[i] = 0u;
   }
-  for (int i = threadIdx.x; i < p.up * kNB; i += kDecThreads) { c_s[i] = 0.0f; hown[i] = __float2bfloat16(0.0f); }
+  for (int i = threadIdx.x; i < p.up * kNB; i += kCThreads) { c_s[i] = 0.0f; hown[i] = __float2bfloat16(0.0f); }
   if (threadIdx.x < kNB) {
     const int b = b0 + threadIdx.x;
     s_t[threadIdx.x] = 0; s_em[threadIdx.x] = 0; s_n[threadIdx.x] = 0;
@@ -546,67 +552,85 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
           tma_load_2d(ring + st * kAStage, tm, &full_bar[st], k * kBK, row0);
         }
       };
+      // Order of the stream == order of the MMA warp: L(0); then per step P(s), L(s+1) tile 0, J(s), L(s+1) tiles 1..
+      auto push_l = [&](int m) { push(&tm_wl, static_cast<int>(rank) * 4 * p.up + m * kBM, p.kbHp); };
+      for (int m = 0; m < p.mtL; ++m) push_l(m);
       for (int s = 0; s <= p.max_steps; ++s) {
-        for (int m = 0; m < p.mtL; ++m) push(&tm_wl, static_cast<int>(rank) * 4 * p.up + m * kBM, p.kbHp);
         const long long t0 = prof ? clock64() : 0;
         if (s > 0) { mbar_wait(step_bar, (s - 1) & 1); if (!s_go[(s - 1) & 1]) break; }
         if (prof) w_step += clock64() - t0;
         for (int m = 0; m < p.mtP; ++m) push(&tm_wp, static_cast<int>(rank) * p.RP + m * kBM, p.kbHp);
+        push_l(0);
         for (int m = 0; m < p.mtJ; ++m) push(&tm_wj, static_cast<int>(rank) * p.RJ + m * kBM, p.kbH);
+        for (int m = 1; m < p.mtL; ++m) push_l(m);
       }
       if (prof) { g_dec_prof[10] = w_empty; g_dec_prof[11] = w_step; }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issue
-    // Converged warp, elect.sync-predicated tcgen05 instructions, running descriptors and a poll-ahead try_wait: under
-    // `if (lane == 0)` ptxas wraps every UTCHMMA in a divergence waterfall that costs ~160 cycles per MMA, 20x the 8
-    // cycles the tensor core needs for a 128 x 16 x 16 product (DESIGN.md finding 2).
+  } else if (warp == 1 || warp == kMma2Warp) {
+    // ------------------------------------------------------------------ MMA issue (two warps)
+    // Two warps issue, k-blocks interleaved, each into its own accumulator (columns [0,16) / [16,32) of the tile's TMEM
+    // slot; the epilogue adds the two; tfull barriers count two arrivals).  The MMAs themselves are free here (skipping
+    // them changes the step by 3 %, `decode_prof` bit 1): what bounds this loop is the weight stream -- TMA latency
+    // under load (~3 k cycles) against the bytes the ring keeps in flight -- so the second warp only shortens the
+    // wait -> fence -> issue -> commit turnaround of a ring slot (scripts/micro/mma_small.cu: ~107 cycles per MMA for
+    // one thread with the ring's bookkeeping, 43 without).  Converged warp + elect.sync throughout: under
+    // `if (lane == 0)` ptxas wraps every UTCHMMA in a divergence waterfall (DESIGN.md finding 5.2; 49 -> 35 ms here).
+    const int w = warp == 1 ? 0 : 1;
     const uint32_t idesc = make_idesc_bf16(kBM, kNB, false, false);
-    const bool prof = p.prof && blockIdx.x == 0 && lane == 0;
+    const bool prof = p.prof && blockIdx.x == 0 && lane == 0 && w == 0;
     long long w_full = 0, w_dep = 0;
     const uint64_t ad0 = make_smem_desc_sw128(smem_u32(ring), 16, 1024);
     const uint32_t fb0 = smem_u32(&full_bar[0]), eb0 = smem_u32(&empty_bar[0]);
     int st = 0;
     uint32_t ph = 0, fb = fb0, eb = eb0;
     uint64_t ad = ad0;
-    bool ready = false;
     auto tile = [&](uint32_t b_base, int kb, int slot) {
       const uint64_t bd0 = make_smem_desc_sw128(b_base, 16, 1024);
-      const uint32_t d_tmem = tmem + slot * kTileCols, tf = smem_u32(&tfull_bar[slot]);
+      const uint32_t d_tmem = tmem + slot * kTileCols + w * kNB, tf = smem_u32(&tfull_bar[slot]);
       for (int k = 0; k < kb; ++k) {
-        if (!ready) {
-          const long long t0 = prof ? clock64() : 0;
-          mbar_wait_addr(fb, ph);
-          if (prof) w_full += clock64() - t0;
-        }
-        tc_fence_after();
-        const uint64_t bd = bd0 + static_cast<uint64_t>(k) * (kKBlk >> 4);
-        if (elect_one()) {
+        if ((k & 1) == w) {
+          {
+            const long long t0 = prof ? clock64() : 0;   // try_wait itself suspends the warp: time the whole wait
+            mbar_wait_addr(fb, ph);
+            if (prof) w_full += clock64() - t0;
+          }
+          tc_fence_after();
+          const uint64_t bd = bd0 + static_cast<uint64_t>(k) * (kKBlk >> 4);
+          if (elect_one()) {
+            if (!(p.prof & 2)) {   // bring-up switch: prof & 2 skips the MMAs (timing experiment, results are garbage)
 #pragma unroll
-          for (int kk = 0; kk < kBK / 16; ++kk) umma_bf16(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-          umma_commit_addr(eb);
-          if (k == kb - 1) umma_commit_addr(tf);
+              for (int kk = 0; kk < kBK / 16; ++kk)
+                umma_bf16(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, (k > w || kk != 0) ? 1u : 0u);
+            }
+            umma_commit_addr(eb);
+          }
+          __syncwarp();
         }
-        __syncwarp();
         if (++st == p.n_stages) { st = 0; ph ^= 1; ad = ad0; fb = fb0; eb = eb0; }
         else { ad += kAStage >> 4; fb += 8; eb += 8; }
-        ready = mbar_try_wait_addr(fb, ph);
       }
+      if (elect_one()) umma_commit_addr(tf);   // this warp's share of the tile (possibly empty when kb == 1) is issued
+      __syncwarp();
     };
+    // W_hh . h(s) -- the product of step s+1's cell -- needs h(s) but not the label emitted at step s (only its epilogue
+    // does), so it is issued speculatively inside step s, in the two gaps in which these warps would otherwise wait for an
+    // exchange: tile 0 while the hj slices travel, the other tiles while the argmax keys travel.
+    for (int m = 0; m < p.mtL; ++m) tile(smem_u32(hb[0]), p.kbHp, m);   // step 0: h(-1) = 0
     for (int s = 0; s <= p.max_steps; ++s) {
-      const int cur = s & 1, nxt = cur ^ 1;
-      for (int m = 0; m < p.mtL; ++m) tile(smem_u32(hb[cur]), p.kbHp, m);   // speculative for s > 0: needs no label
+      const int nxt = (s + 1) & 1;
       long long t0 = prof ? clock64() : 0;
       if (s > 0) { mbar_wait(step_bar, (s - 1) & 1); if (!s_go[(s - 1) & 1]) break; }
       mbar_wait(&hfull_bar[nxt], (s >> 1) & 1);
       if (prof) w_dep += clock64() - t0;
       tc_fence_after();
       for (int m = 0; m < p.mtP; ++m) tile(smem_u32(hb[nxt]), p.kbHp, slotP0 + m);
+      tile(smem_u32(hb[nxt]), p.kbHp, 0);
       t0 = prof ? clock64() : 0;
       mbar_wait(hjfull_bar, s & 1);
       if (prof) w_dep += clock64() - t0;
       tc_fence_after();
       for (int m = 0; m < p.mtJ; ++m) tile(smem_u32(hj), p.kbH, slotJ0 + m);
+      for (int m = 1; m < p.mtL; ++m) tile(smem_u32(hb[nxt]), p.kbHp, m);
     }
     if (prof) { g_dec_prof[12] = w_full; g_dec_prof[13] = w_dep; }
     if (elect_one()) umma_commit(fin_bar);
@@ -615,10 +639,14 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
     tc_fence_after();
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    // Eight warps: two per TMEM lane quadrant, each taking one half of the cluster's 16 utterances (an epilogue warp runs
+    // alone on its scheduler and is latency-bound at ~5 cycles per instruction, so the work is spread, not vectorised).
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;            // utterances [8 half, 8 half + 8)
+    const int n0 = half * kNH;
     const int row = quad * 32 + lane;            // TMEM lane == weight row inside the tile
-    const int et = (warp - 2) * 32 + lane;       // 0..127
-    const uint32_t lane_taddr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    const int et = (warp - 2) * 32 + lane;       // 0..255
+    const uint32_t lane_taddr = tmem + (static_cast<uint32_t>(quad * 32) << 16) + n0;
     const size_t gate_pitch = static_cast<size_t>(4) * p.Hp;
     const uint32_t slice_h = static_cast<uint32_t>(p.up / 64) * kKBlk;
     const uint32_t slice_p = static_cast<uint32_t>(p.RP / 64) * kKBlk;
@@ -628,61 +656,55 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
     long long last = clock64();
     int n_steps = 0;
     for (int s = 0; s <= p.max_steps; ++s) {
-      const int cur = s & 1, nxt = cur ^ 1;
+      const int nxt = (s + 1) & 1;
       const uint32_t par = s & 1;
       ++n_steps;
       // ---------------------------------------------------------------- L: gates -> cell -> h
       for (int m = 0; m < p.mtL; ++m) {
         const int u = static_cast<int>(rank) * p.up + m * 32 + lane;   // this thread: gate `quad` of unit u
-        float tv[kNB];
+        float tv[kNH];
 #pragma unroll
-        for (int n = 0; n < kNB; ++n) {
-          const int lab = s_lab[n];
-          tv[n] = (lab >= 0 && u < p.Hp) ? __ldg(p.table + static_cast<size_t>(lab) * gate_pitch + quad * p.Hp + u) : 0.0f;
+        for (int i = 0; i < kNH; ++i) {
+          const int lab = s_lab[n0 + i];
+          tv[i] = (lab >= 0 && u < p.Hp) ? __ldg(p.table + static_cast<size_t>(lab) * gate_pitch + quad * p.Hp + u) : 0.0f;
         }
         if (m == 0) DSTAMP(0);   // table gather issued
         mbar_wait(&tfull_bar[m], par);
         if (m == 0) DSTAMP(1);   // waited for the L accumulator
         tc_fence_after();
-        float acc_v[kNB];
-        ld_tile_sum(lane_taddr + m * kTileCols, acc_v);
-        float4* gdst = reinterpret_cast<float4*>(gates + (quad * 32 + lane) * kNB);
+        float raw[kNH];
+        ld_acc(lane_taddr + m * kTileCols, p.kbHp > 1, raw);
+        float a[kNH];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float a[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float x = acc_v[4 * q + e] + tv[4 * q + e];
-            a[e] = quad == 2 ? tanh_f(x) : sigmoid_f(x);
-          }
-          gdst[q] = make_float4(a[0], a[1], a[2], a[3]);
+        for (int i = 0; i < kNH; ++i) {
+          const float x = raw[i] + tv[i];
+          a[i] = quad == 2 ? tanh_f(x) : sigmoid_f(x);
         }
-        tc_fence_before();
-        named_bar_sync(1, 128);
-        {
-          const int j = et >> 2, ul = m * 32 + j, n_feat = static_cast<int>(rank) * p.up + ul;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int n = (et & 3) * 4 + q;
-            __nv_bfloat16 hv;
-            if (s_lab[n] >= 0) {
-              const float gi = gates[(0 * 32 + j) * kNB + n], gf = gates[(1 * 32 + j) * kNB + n];
-              const float gg = gates[(2 * 32 + j) * kNB + n], go = gates[(3 * 32 + j) * kNB + n];
-              const float c_new = gf * c_s[ul * kNB + n] + gi * gg;
-              c_s[ul * kNB + n] = c_new;
-              hv = __float2bfloat16_rn(go * tanh_f(c_new));
-              hown[ul * kNB + n] = hv;
-            } else {
-              hv = hown[ul * kNB + n];
-            }
-            if (n_feat >= p.Hp) hv = __float2bfloat16(0.0f);
-            *reinterpret_cast<__nv_bfloat16*>(hb[nxt] + act_offset(n_feat, n)) = hv;
-          }
+        float4* gdst = reinterpret_cast<float4*>(gates + ((m * 4 + quad) * 32 + lane) * kNB + n0);
+        gdst[0] = make_float4(a[0], a[1], a[2], a[3]);
+        gdst[1] = make_float4(a[4], a[5], a[6], a[7]);
+      }
+      tc_fence_before();
+      named_bar_sync(1, kEpiThreads);
+      for (int idx = et; idx < p.mtL * 32 * kNB; idx += kEpiThreads) {   // (tile m, unit j, utterance n), n fastest
+        const int m = idx >> 9, j = (idx >> 4) & 31, n = idx & 15;
+        const int ul = m * 32 + j, n_feat = static_cast<int>(rank) * p.up + ul;
+        __nv_bfloat16 hv;
+        if (s_lab[n] >= 0) {
+          const float* gm = gates + (m * 4 * 32 + j) * kNB + n;
+          const float gi = gm[0], gf = gm[32 * kNB], gg = gm[2 * 32 * kNB], go = gm[3 * 32 * kNB];
+          const float c_new = gf * c_s[ul * kNB + n] + gi * gg;
+          c_s[ul * kNB + n] = c_new;
+          hv = __float2bfloat16_rn(go * tanh_f(c_new));
+          hown[ul * kNB + n] = hv;
+        } else {
+          hv = hown[ul * kNB + n];
         }
-        named_bar_sync(1, 128);
+        if (n_feat >= p.Hp) hv = __float2bfloat16(0.0f);
+        *reinterpret_cast<__nv_bfloat16*>(hb[nxt] + act_offset(n_feat, n)) = hv;
       }
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
       if (et == 0) {
         mbar_arrive_expect_tx(&hfull_bar[nxt], static_cast<uint32_t>(C - 1) * slice_h);
         const uint32_t src = smem_u32(hb[nxt]) + rank * slice_h, bar = smem_u32(&hfull_bar[nxt]);
@@ -696,33 +718,33 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       for (int m = 0; m < p.mtP; ++m) {
         const int lr = m * kBM + row, n_feat = static_cast<int>(rank) * p.RP + lr;
         const bool mine = lr < p.RP, valid = mine && n_feat < p.H;
-        float fv[kNB];
+        float fv[kNH];
 #pragma unroll
-        for (int n = 0; n < kNB; ++n) {
-          const int b = b0 + n;
-          int t = s_t[n];
+        for (int i = 0; i < kNH; ++i) {
+          const int b = b0 + n0 + i;
+          int t = s_t[n0 + i];
           t = t < p.Tmax ? t : p.Tmax - 1;
-          fv[n] = (valid && b < p.B)
+          fv[i] = (valid && b < p.B)
                       ? __bfloat162float(__ldg(p.f + (static_cast<size_t>(b) * p.Tmax + t) * p.H + n_feat)) : 0.0f;
         }
         const float bp = (valid && p.bias_p) ? __ldg(p.bias_p + n_feat) : 0.0f;
         mbar_wait(&tfull_bar[slotP0 + m], par);
         if (m == p.mtP - 1) DSTAMP(3);  // waited for the P accumulator (h exchange + P product)
         tc_fence_after();
-        float acc_v[kNB];
-        ld_tile_sum(lane_taddr + (slotP0 + m) * kTileCols, acc_v);
+        float raw[kNH];
+        ld_acc(lane_taddr + (slotP0 + m) * kTileCols, p.kbHp > 1, raw);
         if (mine) {
 #pragma unroll
-          for (int n = 0; n < kNB; ++n) {
-            const float g = bf16_round_f(acc_v[n] + bp);
-            const float hv = valid ? tanh_approx(fv[n] + g) : 0.0f;
-            *reinterpret_cast<__nv_bfloat16*>(hj + act_offset(n_feat, n)) = __float2bfloat16_rn(hv);
+          for (int i = 0; i < kNH; ++i) {
+            const float g = bf16_round_f(raw[i] + bp);
+            const float hv = valid ? tanh_approx(fv[i] + g) : 0.0f;
+            *reinterpret_cast<__nv_bfloat16*>(hj + act_offset(n_feat, n0 + i)) = __float2bfloat16_rn(hv);
           }
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
       if (et == 0) {
         mbar_arrive_expect_tx(hjfull_bar, static_cast<uint32_t>(C - 1) * slice_p);
         const uint32_t src = smem_u32(hj) + rank * slice_p, bar = smem_u32(hjfull_bar);
@@ -733,7 +755,7 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       }
       DSTAMP(4);  // P epilogue + push issued
       // ---------------------------------------------------------------- J: logits -> argmax
-      unsigned long long best = 0ull;  // lane n < 16 keeps the best key of utterance n over this warp's rows
+      unsigned long long best = 0ull;  // lane i < 8 keeps the best key of utterance n0 + i over this warp's rows
       for (int m = 0; m < p.mtJ; ++m) {
         const int lr = m * kBM + row, v = static_cast<int>(rank) * p.RJ + lr;
         const bool valid = lr < p.RJ && v < p.V;
@@ -741,21 +763,21 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
         mbar_wait(&tfull_bar[slotJ0 + m], par);
         if (m == p.mtJ - 1) DSTAMP(5);  // waited for the J accumulator (hj exchange + J product)
         tc_fence_after();
-        float acc_v[kNB];
-        ld_tile_sum(lane_taddr + (slotJ0 + m) * kTileCols, acc_v);
+        float raw[kNH];
+        ld_acc(lane_taddr + (slotJ0 + m) * kTileCols, p.kbH > 1, raw);
 #pragma unroll
-        for (int n = 0; n < kNB; ++n) {
-          const float z = acc_v[n] + bj;
+        for (int i = 0; i < kNH; ++i) {
+          const float z = raw[i] + bj;
           const uint32_t ob = (valid && z == z) ? ordered_bits(z) : 0u;
           const uint32_t mx = __reduce_max_sync(0xffffffffu, ob);
           const uint32_t mv = __reduce_min_sync(0xffffffffu, (ob == mx && ob != 0u) ? static_cast<uint32_t>(v) : 0xFFFFFFFFu);
           const unsigned long long key = mx ? ((static_cast<unsigned long long>(mx) << 32) | (0xFFFFFFFFu - mv)) : 0ull;
-          if (lane == n && key > best) best = key;
+          if (lane == i && key > best) best = key;
         }
       }
-      if (lane < kNB) part[quad * kNB + lane] = best;
+      if (lane < kNH) part[quad * kNB + n0 + lane] = best;
       tc_fence_before();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
       if (et < kNB) {
         unsigned long long key = part[et];
 #pragma unroll
@@ -793,7 +815,7 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
         const unsigned any = __ballot_sync(0xffffffffu, active);
         if (lane == 0) s_go[par] = any != 0u;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
       if (et == 0) mbar_arrive(step_bar);
       DSTAMP(8);  // bookkeeping
       if (!s_go[par]) break;
@@ -893,7 +915,7 @@ int max_clusters_greedy_decode(int smem_bytes, int C) {
   if (C > 8) cudaFuncSetAttribute(greedy_decode_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C);
-  cfg.blockDim = dim3(kDecThreads);
+  cfg.blockDim = dim3(kCThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -914,7 +936,7 @@ cudaError_t launch_greedy_decode_cluster(const CUtensorMap& tm_wj, const CUtenso
   if (a.C > 8) cudaFuncSetAttribute(greedy_decode_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_clusters * a.C);
-  cfg.blockDim = dim3(kDecThreads);
+  cfg.blockDim = dim3(kCThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];

@@ -16,7 +16,7 @@ lens = torch.full((B,), T, dtype=torch.int32)
 lib = _lib.load()
 for c in [int(x) for x in os.environ.get("CLUSTERS", "8").split(",")]:
     lib.rnnt_debug_set(b"decode_cluster", c)
-    lib.rnnt_debug_set(b"decode_prof", 1)
+    lib.rnnt_debug_set(b"decode_prof", int(os.environ.get("DEC_PROF", 1)))
     for _ in range(2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); out = dec(f, lens); e1.record(); torch.cuda.synchronize()
