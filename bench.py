@@ -171,7 +171,7 @@ def decode_bench(dev):
         n_sym = sum(len(o) for o in out)
     return {"workload": "configs[4]: greedy decode B=128 T=500 V=1024 H=1024 max_symbols_per_step=4, LSTM prediction net "
                         "E=256 Hp=512 (random init)", "ms_per_batch": round(best * 1e3, 2),
-            "utterances_per_s": round(B / best, 1), "symbols_emitted": n_sym, "decode_steps": int(n_sym / B) + T,
+            "utterances_per_s": round(B / best, 1), "symbols_emitted": n_sym, "decode_steps_upper_bound": int(n_sym / B) + T,
             "kernel": "greedy_decode_cluster_kernel (one launch per batch)", "timing": "host wall clock around "
             "RNNTGreedyDecoder.forward incl. the H2D copy of f and the D2H copy of the transcripts, best of 3"}
 

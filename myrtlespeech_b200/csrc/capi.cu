@@ -367,6 +367,8 @@ long long rnnt_debug_get(const char* key) {
   if (!strcmp(key, "max_ctas_fwd_c4")) return max_ctas_fwd_persist(4);
   if (!strcmp(key, "max_ctas_mega_c2")) return max_ctas_bwd_mega(2);
   if (!strcmp(key, "max_ctas_mega_c4")) return max_ctas_bwd_mega(4);
+  if (!strcmp(key, "decode_max_clusters_8")) return max_clusters_greedy_decode(216 * 1024, 8);
+  if (!strcmp(key, "decode_max_clusters_16")) return max_clusters_greedy_decode(216 * 1024, 16);
   return -1;
 }
 

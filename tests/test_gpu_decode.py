@@ -179,3 +179,22 @@ def test_fused_lstm_decode_is_deterministic_and_handles_empty_batch_rows(decode_
     b = dec(f.cuda(), lens)
     assert a == b
     assert a[1] == [] and a[3] == []
+
+
+def test_fused_lstm_decode_at_configs4_widths(decode_variant):
+    """BASELINE.json configs[4] widths (B=128, V=H=1024, max 4 symbols per frame; Hp=512, E=256) on a shorter T: the full
+    batch runs on the GPU (8 clusters / the whole grid), the oracle replays a sample of utterances (they are
+    independent)."""
+    B, T, V, H, Hp, E, S = 128, 16, 1024, 1024, 512, 256, 4
+    joint, pred, f, lens = _lstm_case(13, B, T, V, H, Hp, E, blank_bias=6.0)   # 6 of the 7 sampled rows have clear margins
+    blank = V - 1
+    rows = [0, 15, 16, 37, 64, 90, 127]
+    sub = torch.tensor(rows)
+    want, margins = _oracle_transcripts(joint, pred, f[sub], lens[sub], blank, S)
+    model = RNNT(torch.nn.Identity(), pred, joint).cuda()
+    got = RNNTGreedyDecoder(blank, model, max_symbols_per_step=S)(f.cuda(), lens)
+    clear = [m > MARGIN for m in margins]
+    assert sum(clear) >= 4, "seed produced too many near-ties; pick another"
+    assert [got[r] for r, c in zip(rows, clear) if c] == [w for w, c in zip(want, clear) if c]
+    assert sum(len(g) for g in got) > 0
+    assert all(len(g) <= int(l) * S for g, l in zip(got, lens))

@@ -274,3 +274,31 @@ def test_full_size_properties():
     assert rel(one["loss"], got["loss"][5:6]) < 1e-6
     assert rel(one["df"], got["df"][5:6]) < 1e-5
     assert rel(one["dg"], got["dg"][5:6]) < 1e-5
+
+
+def test_subword_width_against_torchaudio():
+    """Independent implementation at V = H = 1024 (beyond what the numpy oracle checks cheaply): torch joint
+    (Linear(tanh(f + g))) + ``torchaudio.functional.rnnt_loss`` with autograd, fp32, on the same bf16-representable
+    inputs.  The torch path does not round h or dz to bf16, so the bound is the looser "includes bf16" one."""
+    torchaudio = pytest.importorskip("torchaudio")
+    B, T, U, V, H = 3, 48, 17, 1024, 1024
+    f, g, W, bias, y, fl, yl = make(31, B, T, U, V, H, V - 1, True)
+    got = run_cuda(f, g, W, bias, y, fl, yl, V - 1)
+    dev = "cuda"
+    ft, gt, Wt, bt = (x.clone().to(dev).requires_grad_(True) for x in (f, g, W, bias))
+    logits = torch.nn.functional.linear(torch.tanh(ft.unsqueeze(2) + gt.unsqueeze(1)), Wt, bt)
+    try:
+        loss = torchaudio.functional.rnnt_loss(logits, y.to(dev), torch.tensor(fl, dtype=torch.int32, device=dev),
+                                               torch.tensor(yl, dtype=torch.int32, device=dev), blank=V - 1,
+                                               reduction="none")
+        loss.sum().backward()
+    except RuntimeError:   # torchaudio built without its CUDA transducer: use its CPU kernel
+        dev = "cpu"
+        ft, gt, Wt, bt = (x.clone().requires_grad_(True) for x in (f, g, W, bias))
+        logits = torch.nn.functional.linear(torch.tanh(ft.unsqueeze(2) + gt.unsqueeze(1)), Wt, bt)
+        loss = torchaudio.functional.rnnt_loss(logits, y, torch.tensor(fl, dtype=torch.int32),
+                                               torch.tensor(yl, dtype=torch.int32), blank=V - 1, reduction="none")
+        loss.sum().backward()
+    assert rel(got["loss"], loss.detach().cpu().numpy()) < 5e-3
+    for name, t in (("df", ft), ("dg", gt), ("dW", Wt), ("db", bt)):
+        assert rel(got[name], t.grad.cpu().numpy()) < 2e-2, name
