@@ -121,6 +121,19 @@ int rnnt_greedy_decode_lstm(const void* f, const int32_t* lens, const void* W, c
                             int B, int Tmax, int V, int H, int Hp, int blank, int max_symbols, int32_t* sym,
                             int sym_cap, int32_t* n_sym, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same for a stack of 1..3 LSTM layers (torch.nn.LSTM(num_layers=n), unidirectional).  Layer 0 is described as above
+ * (gate_table, W_hh); for the upper layers l = 1..n-1
+ *   W_upper    bf16 [n-1][4*Hp][2*Hp]   [W_ih_l | W_hh_l] side by side (torch layouts)
+ *   bias_upper f32  [n-1][4*Hp]         b_ih_l + b_hh_l
+ * (both may be NULL when n_layers == 1); W_proj projects the top layer.  An utterance that emits blank keeps the state of
+ * every layer. */
+size_t rnnt_greedy_decode_stack_workspace_bytes(int B, int V, int H, int Hp, int n_layers);
+int rnnt_greedy_decode_lstm_stack(const void* f, const int32_t* lens, const void* W, const float* bias,
+                                  const float* gate_table, const void* W_hh, int n_layers, const void* W_upper,
+                                  const float* bias_upper, const void* W_proj, const float* bias_proj, int B, int Tmax,
+                                  int V, int H, int Hp, int blank, int max_symbols, int32_t* sym, int sym_cap,
+                                  int32_t* n_sym, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Debug / test hooks (not part of the drop-in surface). */
 int rnnt_debug_copy_stats(const void* workspace, int B, int Tmax, int Umax, int V, int H, float* lp_blank,
                           float* lp_label, float* c_blank, float* c_label, float* lnp_beta, void* stream);

@@ -285,30 +285,32 @@ DecPlan make_dec_plan(int B, int V, int H, int Hp) {
 // Cluster variant of the decode (decode.cu): rows of each weight matrix split over the C CTAs of a cluster.
 struct CDecPlan {
   int ok;
-  int C, RJ, RP, up, mtJ, mtP, mtL, kbH, kbHp, n_stages, tmem_cols;
-  int o_hj, o_h0, o_h1, o_gates, o_c, o_hown, o_amax, o_part, o_state, o_bars, smem;
-  size_t w_whh, w_total;
+  int C, NL, RJ, RP, up, mtJ, mtP, mtL, kbH, kbHp, n_stages, tmem_cols;
+  int o_hj, o_layers, layer_stride, o_gates, o_amax, o_part, o_state, o_bars, smem;
+  size_t w_whh, w_wup, w_total;
 };
 
-CDecPlan make_cdec_plan(int B, int V, int H, int Hp, int C) {
+CDecPlan make_cdec_plan(int B, int V, int H, int Hp, int C, int NL = 1) {
   CDecPlan d{};
-  if (B < 1 || V < 1 || H < 8 || H % 8 || Hp < 8 || Hp % 8 || C < 1 || C > 16) return d;
+  if (B < 1 || V < 1 || H < 8 || H % 8 || Hp < 8 || Hp % 8 || C < 1 || C > 16 || NL < 1 || NL > 3) return d;
+  d.NL = NL;
   auto up64 = [](int x) { return (x + 63) / 64 * 64; };
   d.C = C;
   d.up = up64((Hp + C - 1) / C); d.RP = up64((H + C - 1) / C); d.RJ = up64((V + C - 1) / C);
   d.mtL = d.up / 32; d.mtP = (d.RP + 127) / 128; d.mtJ = (d.RJ + 127) / 128;
-  if (d.mtL + d.mtP + d.mtJ > 10) return d;
+  const int n_tiles = NL * d.mtL + d.mtP + d.mtJ;
+  if (n_tiles > 10) return d;
   d.kbH = (H + 63) / 64; d.kbHp = (Hp + 63) / 64;
   d.tmem_cols = 32;
-  while (d.tmem_cols < 32 * (d.mtL + d.mtP + d.mtJ)) d.tmem_cols *= 2;   // two partial accumulators x 16 utterances per tile
+  while (d.tmem_cols < 32 * n_tiles) d.tmem_cols *= 2;   // two partial accumulators x 16 utterances per tile
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return static_cast<int>(r); };
   d.o_hj = take(static_cast<size_t>(C) * d.RP / 64 * 2048);
-  d.o_h0 = take(static_cast<size_t>(C) * d.up / 64 * 2048);
-  d.o_h1 = take(static_cast<size_t>(C) * d.up / 64 * 2048);
+  // per layer: two h operand buffers, the cell state and this CTA's own units of h (all multiples of 1 KB: up % 64 == 0)
+  d.layer_stride = static_cast<int>(2 * (static_cast<size_t>(C) * d.up / 64 * 2048) + static_cast<size_t>(d.up) * 16 * 4 +
+                                    static_cast<size_t>(d.up) * 16 * 2);
+  d.o_layers = take(static_cast<size_t>(NL) * d.layer_stride);
   d.o_gates = take(static_cast<size_t>(d.mtL) * 4 * 32 * 16 * sizeof(float));
-  d.o_c = take(static_cast<size_t>(d.up) * 16 * sizeof(float));
-  d.o_hown = take(static_cast<size_t>(d.up) * 16 * 2);
   d.o_amax = take(static_cast<size_t>(C) * 16 * 8);
   d.o_part = take(4 * 16 * 8);
   d.o_state = take(512);
@@ -318,11 +320,11 @@ CDecPlan make_cdec_plan(int B, int V, int H, int Hp, int C) {
   d.n_stages = static_cast<int>((cap - fixed) / 16384);
   if (d.n_stages > 12) d.n_stages = 12;
   const int ring = d.n_stages * 16384;
-  d.o_hj += ring; d.o_h0 += ring; d.o_h1 += ring; d.o_gates += ring; d.o_c += ring; d.o_hown += ring; d.o_amax += ring;
-  d.o_part += ring; d.o_state += ring; d.o_bars += ring;
+  d.o_hj += ring; d.o_layers += ring; d.o_gates += ring; d.o_amax += ring; d.o_part += ring; d.o_state += ring; d.o_bars += ring;
   d.smem = static_cast<int>(fixed) + ring;
   d.w_whh = 0;
-  d.w_total = align_up(2 * static_cast<size_t>(C) * 4 * d.up * Hp, 1024);
+  d.w_wup = align_up(2 * static_cast<size_t>(C) * 4 * d.up * Hp, 1024);
+  d.w_total = d.w_wup + align_up(2 * static_cast<size_t>(NL - 1) * C * 4 * d.up * 2 * d.kbHp * 64, 1024);
   d.ok = 1;
   return d;
 }
@@ -637,49 +639,80 @@ int rnnt_greedy_step(const void* f, const float* g, const void* W, const float* 
   return RNNT_OK;
 }
 
-size_t rnnt_greedy_decode_workspace_bytes(int B, int V, int H, int Hp) {
-  const DecPlan d = make_dec_plan(B, V, H, Hp);
-  const CDecPlan c = make_cdec_plan(B, V, H, Hp, g_decode_cluster);
-  const size_t a = d.ok ? d.w_total : 0, b = c.ok ? c.w_total : 0;
+size_t rnnt_greedy_decode_stack_workspace_bytes(int B, int V, int H, int Hp, int n_layers) {
+  const CDecPlan c = make_cdec_plan(B, V, H, Hp, g_decode_cluster, n_layers);
+  size_t a = 0;
+  if (n_layers == 1) { const DecPlan d = make_dec_plan(B, V, H, Hp); a = d.ok ? d.w_total : 0; }
+  const size_t b = c.ok ? c.w_total : 0;
   return a > b ? a : b;
+}
+
+size_t rnnt_greedy_decode_workspace_bytes(int B, int V, int H, int Hp) {
+  return rnnt_greedy_decode_stack_workspace_bytes(B, V, H, Hp, 1);
 }
 
 int rnnt_greedy_decode_lstm(const void* f, const int32_t* lens, const void* W, const float* bias, const float* gate_table,
                             const void* W_hh, const void* W_proj, const float* bias_proj, int B, int Tmax, int V, int H,
                             int Hp, int blank, int max_symbols, int32_t* sym, int sym_cap, int32_t* n_sym, void* workspace,
                             size_t workspace_bytes, void* stream) {
-  if (B < 1 || Tmax < 1 || V < 1 || sym_cap < 1 || max_symbols < 1)
-    return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d V=%d sym_cap=%d max_symbols=%d out of range", B, Tmax, V, sym_cap, max_symbols);
+  return rnnt_greedy_decode_lstm_stack(f, lens, W, bias, gate_table, W_hh, 1, nullptr, nullptr, W_proj, bias_proj, B, Tmax, V,
+                                       H, Hp, blank, max_symbols, sym, sym_cap, n_sym, workspace, workspace_bytes, stream);
+}
+
+int rnnt_greedy_decode_lstm_stack(const void* f, const int32_t* lens, const void* W, const float* bias,
+                                  const float* gate_table, const void* W_hh, int n_layers, const void* W_upper,
+                                  const float* bias_upper, const void* W_proj, const float* bias_proj, int B, int Tmax, int V,
+                                  int H, int Hp, int blank, int max_symbols, int32_t* sym, int sym_cap, int32_t* n_sym,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 1 || Tmax < 1 || V < 1 || sym_cap < 1 || max_symbols < 1 || n_layers < 1)
+    return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d V=%d sym_cap=%d max_symbols=%d n_layers=%d out of range", B, Tmax, V,
+                sym_cap, max_symbols, n_layers);
   if (blank < 0 || blank >= V) return fail(RNNT_ERR_INVALID_ARGUMENT, "blank=%d must be in [0, %d]", blank, V - 1);
-  if (!f || !lens || !W || !gate_table || !W_hh || !W_proj || !sym || !n_sym || !workspace)
+  if (!f || !lens || !W || !gate_table || !W_hh || !W_proj || !sym || !n_sym || !workspace ||
+      (n_layers > 1 && (!W_upper || !bias_upper)))
     return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  const CDecPlan c = make_cdec_plan(B, V, H, Hp, g_decode_cluster);
-  if (g_decode_variant == 1 && c.ok && workspace_bytes >= c.w_total && max_clusters_greedy_decode(c.smem, c.C) >= 1) {
+  const CDecPlan c = make_cdec_plan(B, V, H, Hp, g_decode_cluster, n_layers);
+  const bool want_cluster = g_decode_variant == 1 || n_layers > 1;   // the grid-barrier schedule is single-layer only
+  if (want_cluster && c.ok && workspace_bytes >= c.w_total && max_clusters_greedy_decode(c.smem, c.C) >= 1) {
     __nv_bfloat16* whh_perm = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* wup_perm = reinterpret_cast<__nv_bfloat16*>(ws + c.w_wup);
     const int rows_l = c.C * 4 * c.up;
     KLAUNCH(K_MISC, s, launch_permute_whh_cluster(static_cast<const __nv_bfloat16*>(W_hh), whh_perm, Hp, c.up, rows_l, s));
-    CUtensorMap tm_wj, tm_wl, tm_wp;
+    if (n_layers > 1)
+      KLAUNCH(K_MISC, s, launch_permute_wup_cluster(static_cast<const __nv_bfloat16*>(W_upper), wup_perm, Hp, c.up, c.C,
+                                                    c.kbHp, (n_layers - 1) * rows_l, s));
+    CUtensorMap tm_wj, tm_wl, tm_wu, tm_wp;
     int rc;
     if ((rc = make_map(&tm_wj, W, H, V, H, 64, 128))) return rc;
     if ((rc = make_map(&tm_wl, whh_perm, Hp, rows_l, Hp, 64, 128))) return rc;
+    if (n_layers > 1) {
+      if ((rc = make_map(&tm_wu, wup_perm, 2 * c.kbHp * 64, static_cast<uint64_t>(n_layers - 1) * rows_l, 2 * c.kbHp * 64, 64, 128)))
+        return rc;
+    } else {
+      tm_wu = tm_wl;   // never dereferenced
+    }
     if ((rc = make_map(&tm_wp, W_proj, Hp, H, Hp, 64, 128))) return rc;
     ClusterDecodeArgs a{};
     a.B = B; a.Tmax = Tmax; a.V = V; a.H = H; a.Hp = Hp; a.blank = blank; a.S = max_symbols; a.sym_cap = sym_cap;
     a.max_steps = Tmax * max_symbols + 1;
     a.C = c.C; a.RJ = c.RJ; a.RP = c.RP; a.up = c.up; a.mtJ = c.mtJ; a.mtP = c.mtP; a.mtL = c.mtL; a.kbH = c.kbH; a.kbHp = c.kbHp;
-    a.n_stages = c.n_stages; a.tmem_cols = c.tmem_cols;
-    a.o_hj = c.o_hj; a.o_h0 = c.o_h0; a.o_h1 = c.o_h1; a.o_gates = c.o_gates; a.o_c = c.o_c; a.o_hown = c.o_hown;
+    a.n_stages = c.n_stages; a.tmem_cols = c.tmem_cols; a.NL = n_layers;
+    a.o_hj = c.o_hj; a.o_layers = c.o_layers; a.layer_stride = c.layer_stride; a.o_gates = c.o_gates;
     a.o_amax = c.o_amax; a.o_part = c.o_part; a.o_state = c.o_state; a.o_bars = c.o_bars;
-    a.f = static_cast<const __nv_bfloat16*>(f); a.lens = lens; a.bias_j = bias; a.table = gate_table; a.bias_p = bias_proj;
+    a.f = static_cast<const __nv_bfloat16*>(f); a.lens = lens; a.bias_j = bias; a.table = gate_table; a.bias_up = bias_upper;
+    a.bias_p = bias_proj;
     a.sym = sym; a.n_sym = n_sym; a.prof = g_decode_prof;
     cudaError_t e = cudaSuccess;
-    KLAUNCH(K_MISC, s, e = launch_greedy_decode_cluster(tm_wj, tm_wl, tm_wp, a, (B + 15) / 16, c.smem, s));
+    KLAUNCH(K_MISC, s, e = launch_greedy_decode_cluster(tm_wj, tm_wl, tm_wu, tm_wp, a, (B + 15) / 16, c.smem, s));
     if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(RNNT_ERR_CUDA, "greedy decode (cluster) launch -> %s", cudaGetErrorString(e)); }
     CUDA_TRY(cudaGetLastError());
     return RNNT_OK;
   }
+  if (n_layers > 1)
+    return fail(RNNT_ERR_UNSUPPORTED, "fused greedy decode does not cover B=%d V=%d H=%d Hp=%d with %d LSTM layers", B, V, H, Hp,
+                n_layers);
   const DecPlan d = make_dec_plan(B, V, H, Hp);
   if (!d.ok) return fail(RNNT_ERR_UNSUPPORTED, "fused greedy decode does not cover B=%d V=%d H=%d Hp=%d", B, V, H, Hp);
   if (workspace_bytes < d.w_total)

@@ -449,7 +449,8 @@ constexpr int kKBlk = kNB * 128;      // bytes of one k-block of an activation b
 constexpr int kCThreads = 352;        // warp 0: TMA, warps 1 and 10: MMA issue, warps 2..9: epilogue
 constexpr int kMma2Warp = 10;
 constexpr int kEpiThreads = 256;
-constexpr int kMaxTiles = 10;         // accumulator tiles (L + P + J) per CTA
+constexpr int kMaxTiles = 10;         // accumulator tiles (L of every layer + P + J) per CTA
+constexpr int kMaxLayers = 3;         // LSTM layers of the prediction network
 constexpr int kTileCols = 2 * kNB;    // TMEM columns per accumulator tile: one partial accumulator per issuing warp.
                                       // (Spreading one warp's MMAs over four accumulators was measured: no change --
                                       // the cost per MMA is issue latency of the thread, not an accumulator dependency.)
@@ -471,15 +472,20 @@ __device__ __forceinline__ uint32_t act_offset(int n, int utt) {  // byte offset
 
 __global__ void __launch_bounds__(kCThreads, 1)
 greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __grid_constant__ CUtensorMap tm_wl,
-                             const __grid_constant__ CUtensorMap tm_wp, const ClusterDecodeArgs p) {
+                             const __grid_constant__ CUtensorMap tm_wu, const __grid_constant__ CUtensorMap tm_wp,
+                             const ClusterDecodeArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
   uint8_t* hj = smem + p.o_hj;
-  uint8_t* hb[2] = {smem + p.o_h0, smem + p.o_h1};
+  // per LSTM layer l: [h buffer 0][h buffer 1][c: up x 16 f32][own units of h: up x 16 bf16], `layer_stride` apart
+  const int n_h_bytes = (p.C * p.up / 64) * kKBlk;
+  auto hbuf = [&](int l, int i) { return smem + p.o_layers + l * p.layer_stride + i * n_h_bytes; };
+  auto cbuf = [&](int l) { return reinterpret_cast<float*>(smem + p.o_layers + l * p.layer_stride + 2 * n_h_bytes); };
+  auto hownbuf = [&](int l) {
+    return reinterpret_cast<__nv_bfloat16*>(smem + p.o_layers + l * p.layer_stride + 2 * n_h_bytes + p.up * kNB * 4);
+  };
   float* gates = reinterpret_cast<float*>(smem + p.o_gates);                 // [mtL][4][32][16]
-  float* c_s = reinterpret_cast<float*>(smem + p.o_c);                       // [up][16]
-  __nv_bfloat16* hown = reinterpret_cast<__nv_bfloat16*>(smem + p.o_hown);   // [up][16]
   unsigned long long* amax_s = reinterpret_cast<unsigned long long*>(smem + p.o_amax);  // [C][16]
   unsigned long long* part = reinterpret_cast<unsigned long long*>(smem + p.o_part);    // [4][16]
   int* s_t = reinterpret_cast<int*>(smem + p.o_state);
@@ -492,8 +498,8 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
   uint64_t* full_bar = bars;                          // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [kMaxTiles]
-  uint64_t* hfull_bar = tfull_bar + kMaxTiles;        // [2]
-  uint64_t* hjfull_bar = hfull_bar + 2;
+  uint64_t* hfull_bar = tfull_bar + kMaxTiles;        // [kMaxLayers][2]
+  uint64_t* hjfull_bar = hfull_bar + 2 * kMaxLayers;
   uint64_t* amaxfull_bar = hjfull_bar + 1;
   uint64_t* step_bar = amaxfull_bar + 1;
   uint64_t* fin_bar = step_bar + 1;
@@ -503,13 +509,13 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
   const uint32_t rank = cluster_ctarank();
   const int C = p.C;
   const int b0 = (blockIdx.x / C) * kNB;
-  const int n_h_bytes = (C * p.up / 64) * kKBlk;
+  const int NL = p.NL;
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&tm_wj); prefetch_tmap(&tm_wl); prefetch_tmap(&tm_wp);
+    prefetch_tmap(&tm_wj); prefetch_tmap(&tm_wl); prefetch_tmap(&tm_wu); prefetch_tmap(&tm_wp);
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < kMaxTiles; ++i) mbar_init(&tfull_bar[i], 2);   // one arrival per issuing warp
-    mbar_init(&hfull_bar[0], 1); mbar_init(&hfull_bar[1], 1);
+    for (int i = 0; i < 2 * kMaxLayers; ++i) mbar_init(&hfull_bar[i], 1);
     mbar_init(hjfull_bar, 1); mbar_init(amaxfull_bar, 1); mbar_init(step_bar, 1); mbar_init(fin_bar, 2);
     fence_barrier_init();
   }
@@ -517,11 +523,8 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < n_h_bytes / 4; i += kCThreads) {
-    reinterpret_cast<uint32_t*>(hb[0])[i] = 0u;   // h_{-1} = 0
-    reinterpret_cast<uint32_t*>(hb[1])[i] = 0u;
-  }
-  for (int i = threadIdx.x; i < p.up * kNB; i += kCThreads) { c_s[i] = 0.0f; hown[i] = __float2bfloat16(0.0f); }
+  for (int i = threadIdx.x; i < NL * p.layer_stride / 4; i += kCThreads)   // h_{-1} = 0, c_{-1} = 0 for every layer
+    reinterpret_cast<uint32_t*>(smem + p.o_layers)[i] = 0u;
   if (threadIdx.x < kNB) {
     const int b = b0 + threadIdx.x;
     s_t[threadIdx.x] = 0; s_em[threadIdx.x] = 0; s_n[threadIdx.x] = 0;
@@ -534,7 +537,7 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
   cluster_sync_all();  // every CTA's barriers and buffers exist before anybody pushes into them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int slotP0 = p.mtL, slotJ0 = p.mtL + p.mtP;
+  const int slotP0 = NL * p.mtL, slotJ0 = NL * p.mtL + p.mtP;   // accumulator slots: layer l tile m = l mtL + m, then P, J
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight stream (runs ahead of the recurrence)
@@ -542,7 +545,7 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       uint32_t it = 0;
       const bool prof = p.prof && blockIdx.x == 0;
       long long w_empty = 0, w_step = 0;
-      auto push = [&](const CUtensorMap* tm, int row0, int kb) {
+      auto push = [&](const CUtensorMap* tm, int row0, int kb) {   // columns k * 64: the upper layers' [W_ih | W_hh] rows too
         for (int k = 0; k < kb; ++k, ++it) {
           const int st = it % p.n_stages;
           const long long t0 = prof ? clock64() : 0;
@@ -552,13 +555,15 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
           tma_load_2d(ring + st * kAStage, tm, &full_bar[st], k * kBK, row0);
         }
       };
-      // Order of the stream == order of the MMA warp: L(0); then per step P(s), L(s+1) tile 0, J(s), L(s+1) tiles 1..
+      // Order of the stream == order of the MMA warps: L0(0); then per step L1(s).., P(s), L0(s+1) tile 0, J(s), L0(s+1) tiles 1..
       auto push_l = [&](int m) { push(&tm_wl, static_cast<int>(rank) * 4 * p.up + m * kBM, p.kbHp); };
       for (int m = 0; m < p.mtL; ++m) push_l(m);
       for (int s = 0; s <= p.max_steps; ++s) {
         const long long t0 = prof ? clock64() : 0;
         if (s > 0) { mbar_wait(step_bar, (s - 1) & 1); if (!s_go[(s - 1) & 1]) break; }
         if (prof) w_step += clock64() - t0;
+        for (int l = 1; l < NL; ++l)
+          for (int m = 0; m < p.mtL; ++m) push(&tm_wu, ((l - 1) * C + static_cast<int>(rank)) * 4 * p.up + m * kBM, 2 * p.kbHp);
         for (int m = 0; m < p.mtP; ++m) push(&tm_wp, static_cast<int>(rank) * p.RP + m * kBM, p.kbHp);
         push_l(0);
         for (int m = 0; m < p.mtJ; ++m) push(&tm_wj, static_cast<int>(rank) * p.RJ + m * kBM, p.kbH);
@@ -584,9 +589,13 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
     int st = 0;
     uint32_t ph = 0, fb = fb0, eb = eb0;
     uint64_t ad = ad0;
-    auto tile = [&](uint32_t b_base, int kb, int slot) {
+    // One accumulator tile over kb + kb1 k-blocks: the first kb against activation buffer b_base, the rest against b_base1
+    // (upper LSTM layers: h of the layer below, then the layer's own previous h).
+    auto tile = [&](uint32_t b_base, int kb0, int slot, uint32_t b_base1 = 0, int kb1 = 0) {
       const uint64_t bd0 = make_smem_desc_sw128(b_base, 16, 1024);
+      const uint64_t bd1 = make_smem_desc_sw128(b_base1, 16, 1024) - static_cast<uint64_t>(kb0) * (kKBlk >> 4);
       const uint32_t d_tmem = tmem + slot * kTileCols + w * kNB, tf = smem_u32(&tfull_bar[slot]);
+      const int kb = kb0 + kb1;
       for (int k = 0; k < kb; ++k) {
         if ((k & 1) == w) {
           {
@@ -595,7 +604,7 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
             if (prof) w_full += clock64() - t0;
           }
           tc_fence_after();
-          const uint64_t bd = bd0 + static_cast<uint64_t>(k) * (kKBlk >> 4);
+          const uint64_t bd = (k < kb0 ? bd0 : bd1) + static_cast<uint64_t>(k) * (kKBlk >> 4);
           if (elect_one()) {
             if (!(p.prof & 2)) {   // bring-up switch: prof & 2 skips the MMAs (timing experiment, results are garbage)
 #pragma unroll
@@ -615,22 +624,29 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
     // W_hh . h(s) -- the product of step s+1's cell -- needs h(s) but not the label emitted at step s (only its epilogue
     // does), so it is issued speculatively inside step s, in the two gaps in which these warps would otherwise wait for an
     // exchange: tile 0 while the hj slices travel, the other tiles while the argmax keys travel.
-    for (int m = 0; m < p.mtL; ++m) tile(smem_u32(hb[0]), p.kbHp, m);   // step 0: h(-1) = 0
+    for (int m = 0; m < p.mtL; ++m) tile(smem_u32(hbuf(0, 0)), p.kbHp, m);   // step 0: h(-1) = 0
     for (int s = 0; s <= p.max_steps; ++s) {
-      const int nxt = (s + 1) & 1;
+      const int cur = s & 1, nxt = cur ^ 1;
+      const uint32_t hpar = (s >> 1) & 1;   // every h buffer is refilled every other step
       long long t0 = prof ? clock64() : 0;
       if (s > 0) { mbar_wait(step_bar, (s - 1) & 1); if (!s_go[(s - 1) & 1]) break; }
-      mbar_wait(&hfull_bar[nxt], (s >> 1) & 1);
+      for (int l = 1; l < NL; ++l) {        // upper layers: W_ih . h_{l-1}(s) + W_hh . h_l(s-1)
+        mbar_wait(&hfull_bar[2 * (l - 1) + nxt], hpar);
+        tc_fence_after();
+        for (int m = 0; m < p.mtL; ++m)
+          tile(smem_u32(hbuf(l - 1, nxt)), p.kbHp, l * p.mtL + m, smem_u32(hbuf(l, cur)), p.kbHp);
+      }
+      mbar_wait(&hfull_bar[2 * (NL - 1) + nxt], hpar);
       if (prof) w_dep += clock64() - t0;
       tc_fence_after();
-      for (int m = 0; m < p.mtP; ++m) tile(smem_u32(hb[nxt]), p.kbHp, slotP0 + m);
-      tile(smem_u32(hb[nxt]), p.kbHp, 0);
+      for (int m = 0; m < p.mtP; ++m) tile(smem_u32(hbuf(NL - 1, nxt)), p.kbHp, slotP0 + m);
+      tile(smem_u32(hbuf(0, nxt)), p.kbHp, 0);
       t0 = prof ? clock64() : 0;
       mbar_wait(hjfull_bar, s & 1);
       if (prof) w_dep += clock64() - t0;
       tc_fence_after();
       for (int m = 0; m < p.mtJ; ++m) tile(smem_u32(hj), p.kbH, slotJ0 + m);
-      for (int m = 1; m < p.mtL; ++m) tile(smem_u32(hb[nxt]), p.kbHp, m);
+      for (int m = 1; m < p.mtL; ++m) tile(smem_u32(hbuf(0, nxt)), p.kbHp, m);
     }
     if (prof) { g_dec_prof[12] = w_full; g_dec_prof[13] = w_dep; }
     if (elect_one()) umma_commit(fin_bar);
@@ -659,58 +675,70 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       const int nxt = (s + 1) & 1;
       const uint32_t par = s & 1;
       ++n_steps;
-      // ---------------------------------------------------------------- L: gates -> cell -> h
-      for (int m = 0; m < p.mtL; ++m) {
-        const int u = static_cast<int>(rank) * p.up + m * 32 + lane;   // this thread: gate `quad` of unit u
-        float tv[kNH];
+      // ---------------------------------------------------------------- L: gates -> cell -> h, layer by layer
+      for (int l = 0; l < NL; ++l) {
+        float* c_s = cbuf(l);
+        __nv_bfloat16* hown = hownbuf(l);
+        uint8_t* hdst = hbuf(l, nxt);
+        for (int m = 0; m < p.mtL; ++m) {
+          const int u = static_cast<int>(rank) * p.up + m * 32 + lane;   // this thread: gate `quad` of unit u
+          float tv[kNH];
+          if (l == 0) {   // embedding + input half of the cell: one table row per emitted label
 #pragma unroll
-        for (int i = 0; i < kNH; ++i) {
-          const int lab = s_lab[n0 + i];
-          tv[i] = (lab >= 0 && u < p.Hp) ? __ldg(p.table + static_cast<size_t>(lab) * gate_pitch + quad * p.Hp + u) : 0.0f;
-        }
-        if (m == 0) DSTAMP(0);   // table gather issued
-        mbar_wait(&tfull_bar[m], par);
-        if (m == 0) DSTAMP(1);   // waited for the L accumulator
-        tc_fence_after();
-        float raw[kNH];
-        ld_acc(lane_taddr + m * kTileCols, p.kbHp > 1, raw);
-        float a[kNH];
+            for (int i = 0; i < kNH; ++i) {
+              const int lab = s_lab[n0 + i];
+              tv[i] = (lab >= 0 && u < p.Hp) ? __ldg(p.table + static_cast<size_t>(lab) * gate_pitch + quad * p.Hp + u) : 0.0f;
+            }
+          } else {
+            const float bu = u < p.Hp ? __ldg(p.bias_up + static_cast<size_t>(l - 1) * gate_pitch + quad * p.Hp + u) : 0.0f;
 #pragma unroll
-        for (int i = 0; i < kNH; ++i) {
-          const float x = raw[i] + tv[i];
-          a[i] = quad == 2 ? tanh_f(x) : sigmoid_f(x);
+            for (int i = 0; i < kNH; ++i) tv[i] = bu;
+          }
+          if (l == 0 && m == 0) DSTAMP(0);   // table gather issued
+          mbar_wait(&tfull_bar[l * p.mtL + m], par);
+          if (l == 0 && m == 0) DSTAMP(1);   // waited for the L accumulator
+          tc_fence_after();
+          float raw[kNH];
+          ld_acc(lane_taddr + (l * p.mtL + m) * kTileCols, l > 0 || p.kbHp > 1, raw);
+          float a[kNH];
+#pragma unroll
+          for (int i = 0; i < kNH; ++i) {
+            const float x = raw[i] + tv[i];
+            a[i] = quad == 2 ? tanh_f(x) : sigmoid_f(x);
+          }
+          float4* gdst = reinterpret_cast<float4*>(gates + ((m * 4 + quad) * 32 + lane) * kNB + n0);
+          gdst[0] = make_float4(a[0], a[1], a[2], a[3]);
+          gdst[1] = make_float4(a[4], a[5], a[6], a[7]);
         }
-        float4* gdst = reinterpret_cast<float4*>(gates + ((m * 4 + quad) * 32 + lane) * kNB + n0);
-        gdst[0] = make_float4(a[0], a[1], a[2], a[3]);
-        gdst[1] = make_float4(a[4], a[5], a[6], a[7]);
-      }
-      tc_fence_before();
-      named_bar_sync(1, kEpiThreads);
-      for (int idx = et; idx < p.mtL * 32 * kNB; idx += kEpiThreads) {   // (tile m, unit j, utterance n), n fastest
-        const int m = idx >> 9, j = (idx >> 4) & 31, n = idx & 15;
-        const int ul = m * 32 + j, n_feat = static_cast<int>(rank) * p.up + ul;
-        __nv_bfloat16 hv;
-        if (s_lab[n] >= 0) {
-          const float* gm = gates + (m * 4 * 32 + j) * kNB + n;
-          const float gi = gm[0], gf = gm[32 * kNB], gg = gm[2 * 32 * kNB], go = gm[3 * 32 * kNB];
-          const float c_new = gf * c_s[ul * kNB + n] + gi * gg;
-          c_s[ul * kNB + n] = c_new;
-          hv = __float2bfloat16_rn(go * tanh_f(c_new));
-          hown[ul * kNB + n] = hv;
-        } else {
-          hv = hown[ul * kNB + n];
+        tc_fence_before();
+        named_bar_sync(1, kEpiThreads);
+        for (int idx = et; idx < p.mtL * 32 * kNB; idx += kEpiThreads) {   // (tile m, unit j, utterance n), n fastest
+          const int m = idx >> 9, j = (idx >> 4) & 31, n = idx & 15;
+          const int ul = m * 32 + j, n_feat = static_cast<int>(rank) * p.up + ul;
+          __nv_bfloat16 hv;
+          if (s_lab[n] >= 0) {
+            const float* gm = gates + (m * 4 * 32 + j) * kNB + n;
+            const float gi = gm[0], gf = gm[32 * kNB], gg = gm[2 * 32 * kNB], go = gm[3 * 32 * kNB];
+            const float c_new = gf * c_s[ul * kNB + n] + gi * gg;
+            c_s[ul * kNB + n] = c_new;
+            hv = __float2bfloat16_rn(go * tanh_f(c_new));
+            hown[ul * kNB + n] = hv;
+          } else {
+            hv = hown[ul * kNB + n];
+          }
+          if (n_feat >= p.Hp) hv = __float2bfloat16(0.0f);
+          *reinterpret_cast<__nv_bfloat16*>(hdst + act_offset(n_feat, n)) = hv;
         }
-        if (n_feat >= p.Hp) hv = __float2bfloat16(0.0f);
-        *reinterpret_cast<__nv_bfloat16*>(hb[nxt] + act_offset(n_feat, n)) = hv;
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1, kEpiThreads);
-      if (et == 0) {
-        mbar_arrive_expect_tx(&hfull_bar[nxt], static_cast<uint32_t>(C - 1) * slice_h);
-        const uint32_t src = smem_u32(hb[nxt]) + rank * slice_h, bar = smem_u32(&hfull_bar[nxt]);
-        for (int d = 1; d < C; ++d) {
-          const uint32_t dst = (rank + d) % C;
-          bulk_copy_to_cluster(mapa_u32(src, dst), src, slice_h, mapa_u32(bar, dst));
+        fence_proxy_async_smem();
+        named_bar_sync(1, kEpiThreads);   // also: nobody still reads `gates` when the next layer overwrites it
+        if (et == 0) {
+          uint64_t* hf = &hfull_bar[2 * l + nxt];
+          mbar_arrive_expect_tx(hf, static_cast<uint32_t>(C - 1) * slice_h);
+          const uint32_t src = smem_u32(hdst) + rank * slice_h, bar = smem_u32(hf);
+          for (int d = 1; d < C; ++d) {
+            const uint32_t dst = (rank + d) % C;
+            bulk_copy_to_cluster(mapa_u32(src, dst), src, slice_h, mapa_u32(bar, dst));
+          }
         }
       }
       DSTAMP(2);  // L epilogue + push issued
@@ -855,6 +883,26 @@ __global__ void permute_whh_cluster_kernel(const __nv_bfloat16* __restrict__ W, 
   }
 }
 
+// Upper LSTM layers: W_upper [NL-1][4 Hp][2 Hp] = [W_ih_l | W_hh_l] (torch layouts) -> rows [l-1][rank][tile][gate][32 units] as
+// above, columns [W_ih_l | 0-pad to kb*64 | W_hh_l | 0-pad to kb*64] so that both halves start on a k-block boundary.
+__global__ void permute_wup_cluster_kernel(const __nv_bfloat16* __restrict__ W, __nv_bfloat16* __restrict__ out, int Hp,
+                                           int up, int C, int kb, int n_rows) {
+  const int R = blockIdx.x;
+  if (R >= n_rows) return;
+  const int per_rank = 4 * up, per_layer = C * per_rank;
+  const int l1 = R / per_layer, r2 = R - l1 * per_layer;
+  const int rank = r2 / per_rank, rem = r2 - rank * per_rank;
+  const int m = rem >> 7, gate = (rem >> 5) & 3, j = rem & 31;
+  const int u = rank * up + m * 32 + j;
+  const int half_cols = kb * 64;
+  __nv_bfloat16* dst = out + static_cast<size_t>(R) * 2 * half_cols;
+  const __nv_bfloat16* src = W + (static_cast<size_t>(l1) * 4 * Hp + static_cast<size_t>(gate) * Hp + u) * 2 * Hp;
+  for (int c = threadIdx.x; c < 2 * half_cols; c += blockDim.x) {
+    const int half = c / half_cols, cc = c - half * half_cols;
+    dst[c] = (u < Hp && cc < Hp) ? src[half * Hp + cc] : __float2bfloat16(0.0f);
+  }
+}
+
 namespace {
 bool g_decode_cooperative = true;
 }
@@ -902,6 +950,11 @@ void launch_permute_whh_cluster(const __nv_bfloat16* W, __nv_bfloat16* out, int 
   permute_whh_cluster_kernel<<<n_rows, 128, 0, s>>>(W, out, Hp, up, n_rows);
 }
 
+void launch_permute_wup_cluster(const __nv_bfloat16* W, __nv_bfloat16* out, int Hp, int up, int C, int kb, int n_rows,
+                                cudaStream_t s) {
+  permute_wup_cluster_kernel<<<n_rows, 128, 0, s>>>(W, out, Hp, up, C, kb, n_rows);
+}
+
 int read_decode_prof(unsigned long long* out, int n) {
   if (n > 16) n = 16;
   return cudaMemcpyFromSymbol(out, g_dec_prof, sizeof(unsigned long long) * n) == cudaSuccess ? n : -1;
@@ -929,8 +982,9 @@ int max_clusters_greedy_decode(int smem_bytes, int C) {
   return n;
 }
 
-cudaError_t launch_greedy_decode_cluster(const CUtensorMap& tm_wj, const CUtensorMap& tm_wl, const CUtensorMap& tm_wp,
-                                         const ClusterDecodeArgs& a, int n_clusters, int smem_bytes, cudaStream_t s) {
+cudaError_t launch_greedy_decode_cluster(const CUtensorMap& tm_wj, const CUtensorMap& tm_wl, const CUtensorMap& tm_wu,
+                                         const CUtensorMap& tm_wp, const ClusterDecodeArgs& a, int n_clusters, int smem_bytes,
+                                         cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(greedy_decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
   if (a.C > 8) cudaFuncSetAttribute(greedy_decode_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -943,7 +997,7 @@ cudaError_t launch_greedy_decode_cluster(const CUtensorMap& tm_wj, const CUtenso
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = a.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, greedy_decode_cluster_kernel, tm_wj, tm_wl, tm_wp, a);
+  return cudaLaunchKernelEx(&cfg, greedy_decode_cluster_kernel, tm_wj, tm_wl, tm_wu, tm_wp, a);
 }
 
 }  // namespace rnnt

@@ -192,11 +192,13 @@ struct ClusterDecodeArgs {
   int mtJ, mtP, mtL;       // 128-row accumulator tiles per CTA and product
   int kbH, kbHp;           // k-blocks over H / Hp
   int n_stages, tmem_cols;
-  int o_hj, o_h0, o_h1, o_gates, o_c, o_hown, o_amax, o_part, o_state, o_bars;
+  int NL;                  // LSTM layers of the prediction network (1..3)
+  int o_hj, o_layers, layer_stride, o_gates, o_amax, o_part, o_state, o_bars;
   const __nv_bfloat16* f;
   const int* lens;
   const float* bias_j;
   const float* table;
+  const float* bias_up;    // [NL-1][4 Hp]  b_ih + b_hh of the upper layers
   const float* bias_p;
   int* sym;
   int* n_sym;
@@ -205,8 +207,11 @@ struct ClusterDecodeArgs {
 int read_decode_prof(unsigned long long* out, int n);
 void launch_permute_whh_cluster(const __nv_bfloat16* W, __nv_bfloat16* out, int Hp, int up, int n_rows, cudaStream_t s);
 int max_clusters_greedy_decode(int smem_bytes, int C);
-cudaError_t launch_greedy_decode_cluster(const CUtensorMap& tm_wj, const CUtensorMap& tm_wl, const CUtensorMap& tm_wp,
-                                         const ClusterDecodeArgs& a, int n_clusters, int smem_bytes, cudaStream_t s);
+void launch_permute_wup_cluster(const __nv_bfloat16* W, __nv_bfloat16* out, int Hp, int up, int C, int kb, int n_rows,
+                                cudaStream_t s);
+cudaError_t launch_greedy_decode_cluster(const CUtensorMap& tm_wj, const CUtensorMap& tm_wl, const CUtensorMap& tm_wu,
+                                         const CUtensorMap& tm_wp, const ClusterDecodeArgs& a, int n_clusters, int smem_bytes,
+                                         cudaStream_t s);
 
 
 void set_gemm_dbg(int v);

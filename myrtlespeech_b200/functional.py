@@ -157,34 +157,41 @@ def greedy_step(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: Optiona
                                     B, Tmax, V, H, int(blank), int(max_symbols), _stream()))
 
 
-def greedy_decode_lstm_supported(B: int, V: int, H: int, Hp: int) -> bool:
-    """Whether the one-launch decode (``rnnt_greedy_decode_lstm``) covers this shape."""
-    return _lib.load().rnnt_greedy_decode_workspace_bytes(B, V, H, Hp) > 0
+def greedy_decode_lstm_supported(B: int, V: int, H: int, Hp: int, n_layers: int = 1) -> bool:
+    """Whether the one-launch decode (``rnnt_greedy_decode_lstm_stack``) covers this shape."""
+    return _lib.load().rnnt_greedy_decode_stack_workspace_bytes(B, V, H, Hp, n_layers) > 0
 
 
 def greedy_decode_lstm(f: torch.Tensor, lens: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor],
                        gate_table: torch.Tensor, W_hh: torch.Tensor, W_proj: torch.Tensor,
-                       bias_proj: Optional[torch.Tensor], blank: int, max_symbols: int):
-    """Whole greedy decode of a batch in one launch (see ``rnnt_greedy_decode_lstm`` in include/rnnt_b200.h).
+                       bias_proj: Optional[torch.Tensor], blank: int, max_symbols: int,
+                       W_upper: Optional[torch.Tensor] = None, bias_upper: Optional[torch.Tensor] = None):
+    """Whole greedy decode of a batch in one launch (see ``rnnt_greedy_decode_lstm_stack`` in include/rnnt_b200.h).
 
     f bf16 (B,T,H); lens int32 (B) on the device; W bf16 (V,H); gate_table fp32 (V+1, 4*Hp); W_hh bf16 (4*Hp, Hp);
-    W_proj bf16 (H, Hp).  Returns ``(sym int32 (B, T*max_symbols), n_sym int32 (B))`` on the device.
+    W_proj bf16 (H, Hp); for an n-layer LSTM ``W_upper`` bf16 (n-1, 4*Hp, 2*Hp) = [W_ih_l | W_hh_l] and ``bias_upper``
+    fp32 (n-1, 4*Hp).  Returns ``(sym int32 (B, T*max_symbols), n_sym int32 (B))`` on the device.
     """
     lib = _lib.load()
     B, Tmax, H = f.shape
     V = W.shape[0]
     Hp = W_hh.shape[1]
+    n_layers = 1 if W_upper is None else W_upper.shape[0] + 1
     if gate_table.shape != (V + 1, 4 * Hp) or W_hh.shape[0] != 4 * Hp or tuple(W_proj.shape) != (H, Hp):
         raise ValueError(f"gate_table {tuple(gate_table.shape)}, W_hh {tuple(W_hh.shape)}, W_proj {tuple(W_proj.shape)} "
                          f"do not match V={V} H={H} Hp={Hp}")
-    nbytes = lib.rnnt_greedy_decode_workspace_bytes(B, V, H, Hp)
+    if W_upper is not None and (tuple(W_upper.shape[1:]) != (4 * Hp, 2 * Hp) or bias_upper is None
+                                or tuple(bias_upper.shape) != (n_layers - 1, 4 * Hp)):
+        raise ValueError(f"W_upper {tuple(W_upper.shape)} / bias_upper do not match Hp={Hp}")
+    nbytes = lib.rnnt_greedy_decode_stack_workspace_bytes(B, V, H, Hp, n_layers)
     if nbytes == 0:
-        raise ValueError(f"fused greedy decode does not cover B={B} V={V} H={H} Hp={Hp}")
+        raise ValueError(f"fused greedy decode does not cover B={B} V={V} H={H} Hp={Hp} n_layers={n_layers}")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=f.device)
     cap = max(1, Tmax * max_symbols)
     sym = torch.zeros(B, cap, dtype=torch.int32, device=f.device)
     n_sym = torch.zeros(B, dtype=torch.int32, device=f.device)
-    _lib.check(lib.rnnt_greedy_decode_lstm(_ptr(f), _ptr(lens), _ptr(W), _ptr(bias), _ptr(gate_table), _ptr(W_hh),
-                                           _ptr(W_proj), _ptr(bias_proj), B, Tmax, V, H, Hp, int(blank),
-                                           int(max_symbols), _ptr(sym), cap, _ptr(n_sym), _ptr(ws), nbytes, _stream()))
+    _lib.check(lib.rnnt_greedy_decode_lstm_stack(_ptr(f), _ptr(lens), _ptr(W), _ptr(bias), _ptr(gate_table), _ptr(W_hh),
+                                                 n_layers, _ptr(W_upper), _ptr(bias_upper), _ptr(W_proj), _ptr(bias_proj),
+                                                 B, Tmax, V, H, Hp, int(blank), int(max_symbols), _ptr(sym), cap,
+                                                 _ptr(n_sym), _ptr(ws), nbytes, _stream()))
     return sym, n_sym

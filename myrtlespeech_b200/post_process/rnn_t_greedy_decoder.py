@@ -99,8 +99,9 @@ class RNNTGreedyDecoder(torch.nn.Module):
         if self.USE_FUSED_LOOP and T > 0:
             packed = _pack_lstm_prediction(pred, B, Wb.size(0), H)
             if packed is not None:
-                table, whh, wproj, bproj = packed
-                sym, n_sym = greedy_decode_lstm(fb, lens.contiguous(), Wb, bias, table, whh, wproj, bproj, blank, S)
+                table, whh, wproj, bproj, wup, bup = packed
+                sym, n_sym = greedy_decode_lstm(fb, lens.contiguous(), Wb, bias, table, whh, wproj, bproj, blank, S,
+                                                W_upper=wup, bias_upper=bup)
                 sym_h, n_h = sym.cpu(), n_sym.cpu().tolist()
                 return [sym_h[b, : n_h[b]].tolist() for b in range(B)]
 
@@ -146,20 +147,20 @@ class RNNTGreedyDecoder(torch.nn.Module):
 
 
 def _pack_lstm_prediction(pred, B: int, V: int, H: int):
-    """``(gate_table, W_hh, W_proj, b_proj)`` for the one-launch decode, or None if ``pred`` is not an embedding +
-    single-layer unidirectional LSTM + projection (``RNNTPredictionNet`` layout) the fused kernel covers.
+    """``(gate_table, W_hh, W_proj, b_proj, W_upper, bias_upper)`` for the one-launch decode, or None if ``pred`` is not an
+    embedding + unidirectional LSTM of 1..3 layers + projection (``RNNTPredictionNet`` layout) the fused kernel covers.
 
     ``gate_table[v] = W_ih . emb[v] + b_ih + b_hh`` (fp32) folds the embedding lookup and the input half of the cell
     into one row gather per emitted label; row ``vocab_size`` is the start-of-sequence input."""
     emb, rnn, proj = getattr(pred, "embedding", None), getattr(pred, "rnn", None), getattr(pred, "proj", None)
     if not (isinstance(emb, torch.nn.Embedding) and isinstance(rnn, torch.nn.LSTM) and isinstance(proj, torch.nn.Linear)):
         return None
-    if rnn.num_layers != 1 or rnn.bidirectional or getattr(rnn, "proj_size", 0) != 0:
+    if rnn.num_layers > 3 or rnn.bidirectional or getattr(rnn, "proj_size", 0) != 0:
         return None
     if emb.num_embeddings != V + 1 or proj.out_features != H or not emb.weight.is_cuda:
         return None
     Hp = rnn.hidden_size
-    if not greedy_decode_lstm_supported(B, V, H, Hp):
+    if not greedy_decode_lstm_supported(B, V, H, Hp, rnn.num_layers):
         return None
     table = emb.weight.detach().float() @ rnn.weight_ih_l0.detach().float().t()
     if rnn.bias:
@@ -167,7 +168,16 @@ def _pack_lstm_prediction(pred, B: int, V: int, H: int):
     whh = rnn.weight_hh_l0.detach().to(torch.bfloat16).contiguous()
     wproj = proj.weight.detach().to(torch.bfloat16).contiguous()
     bproj = None if proj.bias is None else proj.bias.detach().float().contiguous()
-    return table.contiguous(), whh, wproj, bproj
+    wup = bup = None
+    if rnn.num_layers > 1:   # upper layers: [W_ih_l | W_hh_l] side by side, summed biases
+        wup = torch.stack([torch.cat([getattr(rnn, f"weight_ih_l{l}").detach(), getattr(rnn, f"weight_hh_l{l}").detach()], 1)
+                           for l in range(1, rnn.num_layers)]).to(torch.bfloat16).contiguous()
+        if rnn.bias:
+            bup = torch.stack([getattr(rnn, f"bias_ih_l{l}").detach().float() + getattr(rnn, f"bias_hh_l{l}").detach().float()
+                               for l in range(1, rnn.num_layers)]).contiguous()
+        else:
+            bup = torch.zeros(rnn.num_layers - 1, 4 * Hp, device=wup.device)
+    return table.contiguous(), whh, wproj, bproj, wup, bup
 
 
 def _clone_hidden(h):

@@ -340,20 +340,29 @@ def lstm_pred_step(
     table, ``h`` and ``W_hh`` / ``W_proj`` are bf16 operands of an fp32-accumulating product, ``c`` stays fp32 and the
     projected ``g`` is rounded to bf16.
     """
+    # a stack of layers is given as lists (one entry per layer); a single layer may be given bare
+    if not isinstance(w_ih, (list, tuple)):
+        w_ih, w_hh, b_ih, b_hh = [w_ih], [w_hh], [b_ih], [b_hh]
+    n_layers = len(w_ih)
     emb = np.asarray(emb, dtype=np.float64)
-    w_ih = np.asarray(w_ih, dtype=np.float64)
-    w_hh = np.asarray(w_hh, dtype=np.float64)
+    w_ih = [np.asarray(w, dtype=np.float64) for w in w_ih]
+    w_hh = [np.asarray(w, dtype=np.float64) for w in w_hh]
     w_proj = np.asarray(w_proj, dtype=np.float64)
-    hp = w_hh.shape[1]
-    bias = np.zeros(4 * hp)
-    if b_ih is not None:
-        bias = bias + np.asarray(b_ih, dtype=np.float64)
-    if b_hh is not None:
-        bias = bias + np.asarray(b_hh, dtype=np.float64)
-    table = emb @ w_ih.T + bias
+    hp = w_hh[0].shape[1]
+    biases = []
+    for l in range(n_layers):
+        bias = np.zeros(4 * hp)
+        if b_ih[l] is not None:
+            bias = bias + np.asarray(b_ih[l], dtype=np.float64)
+        if b_hh[l] is not None:
+            bias = bias + np.asarray(b_hh[l], dtype=np.float64)
+        biases.append(bias)
+    table = emb @ w_ih[0].T + biases[0]
     if faithful:
         table = table.astype(np.float32).astype(np.float64)
-        w_hh = bf16_round(w_hh)
+        biases = [b.astype(np.float32).astype(np.float64) for b in biases]
+        w_hh = [bf16_round(w) for w in w_hh]
+        w_ih = [w_ih[0]] + [bf16_round(w) for w in w_ih[1:]]   # upper layers consume bf16 h of the layer below
         w_proj = bf16_round(w_proj)
     bp = np.zeros(w_proj.shape[0]) if b_proj is None else np.asarray(b_proj, dtype=np.float64)
     sos = emb.shape[0] - 1
@@ -362,17 +371,27 @@ def lstm_pred_step(
         return 1.0 / (1.0 + np.exp(-x))
 
     def step(label: Optional[int], state):
-        h, c = (np.zeros(hp), np.zeros(hp)) if state is None else state
-        a = table[sos if label is None else int(label)] + w_hh @ h
-        i, f, g, o = a[:hp], a[hp:2 * hp], a[2 * hp:3 * hp], a[3 * hp:]
-        c = sigmoid(f) * c + sigmoid(i) * np.tanh(g)
-        h = sigmoid(o) * np.tanh(c)
-        if faithful:
-            c = c.astype(np.float32).astype(np.float64)
-            h = bf16_round(h)
-        out = w_proj @ h + bp
+        if state is None:
+            state = [(np.zeros(hp), np.zeros(hp)) for _ in range(n_layers)]
+        new_state = []
+        x = None
+        for l in range(n_layers):
+            h, c = state[l]
+            if l == 0:
+                a = table[sos if label is None else int(label)] + w_hh[0] @ h
+            else:
+                a = biases[l] + w_ih[l] @ x + w_hh[l] @ h
+            i, f, g, o = a[:hp], a[hp:2 * hp], a[2 * hp:3 * hp], a[3 * hp:]
+            c = sigmoid(f) * c + sigmoid(i) * np.tanh(g)
+            h = sigmoid(o) * np.tanh(c)
+            if faithful:
+                c = c.astype(np.float32).astype(np.float64)
+                h = bf16_round(h)
+            new_state.append((h, c))
+            x = h
+        out = w_proj @ x + bp
         if faithful:
             out = bf16_round(out)
-        return out, (h, c)
+        return out, new_state
 
     return step

@@ -99,11 +99,11 @@ def test_greedy_decoder_constructed_path():
 # --------------------------------------------------------------------------------------------------------------------
 # one-launch decode: LSTM prediction cell + projection + joint argmax + bookkeeping looped on the device
 # --------------------------------------------------------------------------------------------------------------------
-def _lstm_case(seed, B, T, V, H, Hp, E, lens=None, blank_bias=2.5):
+def _lstm_case(seed, B, T, V, H, Hp, E, lens=None, blank_bias=2.5, n_layers=1):
     """Seeded model + inputs (CPU generator, so the GPU box and the CPU container see the same numbers)."""
     torch.manual_seed(seed)
     joint = RNNTJoint(H, V)
-    pred = RNNTPredictionNet(V, E, Hp, 1, H)
+    pred = RNNTPredictionNet(V, E, Hp, n_layers, H)
     with torch.no_grad():
         joint.fc.weight.mul_(4.0)   # spread the logits so that argmax margins are far above bf16 noise
         pred.proj.weight.mul_(3.0)
@@ -119,8 +119,10 @@ def _lstm_case(seed, B, T, V, H, Hp, E, lens=None, blank_bias=2.5):
 
 def _oracle_transcripts(joint, pred, f, lens, blank, S):
     n = lambda t: None if t is None else t.detach().cpu().float().numpy()  # noqa: E731
-    step = O.lstm_pred_step(n(pred.embedding.weight), n(pred.rnn.weight_ih_l0), n(pred.rnn.weight_hh_l0),
-                            n(pred.rnn.bias_ih_l0), n(pred.rnn.bias_hh_l0), n(pred.proj.weight), n(pred.proj.bias),
+    r, L = pred.rnn, range(pred.rnn.num_layers)
+    step = O.lstm_pred_step(n(pred.embedding.weight), [n(getattr(r, f"weight_ih_l{l}")) for l in L],
+                            [n(getattr(r, f"weight_hh_l{l}")) for l in L], [n(getattr(r, f"bias_ih_l{l}")) for l in L],
+                            [n(getattr(r, f"bias_hh_l{l}")) for l in L], n(pred.proj.weight), n(pred.proj.bias),
                             faithful=True)
     return O.greedy_decode(f.float().numpy(), lens.numpy(), n(joint.fc.weight), n(joint.fc.bias), step, blank, S,
                            faithful=True, per_utterance_margin=True)
@@ -198,3 +200,32 @@ def test_fused_lstm_decode_at_configs4_widths(decode_variant):
     assert [got[r] for r, c in zip(rows, clear) if c] == [w for w, c in zip(want, clear) if c]
     assert sum(len(g) for g in got) > 0
     assert all(len(g) <= int(l) * S for g, l in zip(got, lens))
+
+
+STACK_CASES = [
+    # seed, B, T, V, H, Hp, E, S, layers
+    (7, 5, 19, 40, 64, 64, 32, 2, 2),
+    (7, 20, 11, 300, 192, 200, 24, 3, 2),   # two clusters, Hp not a multiple of 64: padded k-block halves
+    (6, 6, 13, 29, 128, 72, 16, 2, 3),
+]
+
+
+@pytest.mark.parametrize("seed,B,T,V,H,Hp,E,S,layers", STACK_CASES)
+def test_fused_stacked_lstm_decode_matches_oracle(seed, B, T, V, H, Hp, E, S, layers):
+    """Prediction networks with 2 and 3 LSTM layers through the one-launch cluster kernel."""
+    joint, pred, f, lens = _lstm_case(seed, B, T, V, H, Hp, E, n_layers=layers)
+    blank = V - 1
+    want, margins = _oracle_transcripts(joint, pred, f, lens, blank, S)
+    clear = [m > MARGIN for m in margins]
+    assert sum(clear) >= 0.6 * B, "seed produced too many near-ties; pick another"
+    model = RNNT(torch.nn.Identity(), pred, joint).cuda()
+    import myrtlespeech_b200.post_process.rnn_t_greedy_decoder as D
+    calls, orig = [], D.greedy_decode_lstm
+    D.greedy_decode_lstm = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        got = RNNTGreedyDecoder(blank, model, max_symbols_per_step=S)(f.cuda(), lens)
+    finally:
+        D.greedy_decode_lstm = orig
+    assert calls, "the one-launch decode was not taken"
+    assert [g for g, c in zip(got, clear) if c] == [w for w, c in zip(want, clear) if c]
+    assert any(len(s) > 0 for s in got)
