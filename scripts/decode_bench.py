@@ -25,7 +25,7 @@ from myrtlespeech_b200 import _lib
 for fused in (("cluster", "gridsync", False) if LAYERS == 1 else ("cluster", False)):
     dec.USE_FUSED_LOOP = bool(fused)
     _lib.load().rnnt_debug_set(b"decode_variant", 1 if fused == "cluster" else 0)
-    for it in range(3):
+    for it in range(int(os.environ.get("PASSES", 3))):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); t0 = time.perf_counter(); e0.record()
         out = dec(f, lens)
