@@ -206,7 +206,8 @@ def test_known_answer_vector_through_lattice_entry():
     assert np.allclose(zt.grad.cpu().numpy(), dz, atol=1e-6)
 
 
-@pytest.mark.parametrize("shape", [(3, 7, 4, 6, 5), (4, 40, 17, 9, 8), (2, 33, 0, 4, 0), (2, 300, 120, 5, 4)])
+@pytest.mark.parametrize("shape", [(3, 7, 4, 6, 5), (4, 40, 17, 9, 8), (2, 33, 0, 4, 0), (2, 300, 120, 5, 4),
+                                   (3, 130, 127, 4, 3), (2, 90, 128, 4, 0), (5, 1, 9, 3, 1)])
 def test_lattice_entry_matches_oracle(shape):
     B, T, U, V, blank = shape
     rng = np.random.default_rng(B * 100 + T)
