@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the configs[4] greedy-decode measurement")
+    ap.add_argument("--ragged", action="store_true",
+                    help="SURVEY.md 8(d) secondary run: T_b ~ U[T/2, T], U_b ~ U[U/2, U], sorted by T_b descending")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -221,6 +223,13 @@ def main():
     peaks = load_peaks()
 
     f, g, W, bias, y, fl, yl = synth(B, T, U, V, H, 1234 + rank, dev)
+    if args.ragged:   # the reference's collate sorts a batch by length (data/batch.py:97-100)
+        gen = torch.Generator().manual_seed(4321 + rank)
+        fl = torch.randint(T // 2, T + 1, (B,), generator=gen, dtype=torch.int32).sort(descending=True).values
+        yl = torch.randint(U // 2, U + 1, (B,), generator=gen, dtype=torch.int32)
+        fl[0] = T
+        yl[0] = U
+        desc += " (ragged: T_b ~ U[T/2, T], U_b ~ U[U/2, U])"
     blank = V - 1
     fd, gd, yd = f.to(dev), g.to(dev), y.to(dev)
     Wd = W.to(dev).requires_grad_(True)
@@ -333,7 +342,7 @@ def main():
     ms_total, e2e_ms = t.tolist()
 
     if rank == 0:
-        n_rows = B * T * (U + 1)
+        n_rows = int((fl.long() * (yl.long() + 1)).sum())   # = B*T*(U+1) for the full-length primary run
         # ALGORITHMIC flops per kernel class (forward 2NHV, backward 4NHV; the logits recompute of the
         # backward pass is extra hardware work and is reported separately as hw_tflops)
         nhv = float(n_rows) * H * V
