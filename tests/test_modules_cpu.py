@@ -55,6 +55,26 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
         _lib.check(rc)
 
 
+def test_decode_abi_workspace_arithmetic_and_argument_checks():
+    """The one-launch decode entry points: workspace sizes are pure host arithmetic, unsupported shapes report 0 and
+    bad arguments are rejected before any CUDA call."""
+    lib = _lib.load()
+    one = lib.rnnt_greedy_decode_workspace_bytes(128, 1024, 1024, 512)
+    two = lib.rnnt_greedy_decode_stack_workspace_bytes(128, 1024, 1024, 512, 2)
+    assert 0 < one < two < 1 << 28
+    assert lib.rnnt_greedy_decode_stack_workspace_bytes(128, 1024, 1024, 512, 1) == one
+    assert lib.rnnt_greedy_decode_workspace_bytes(128, 1024, 1024, 500) == 0        # Hp % 8
+    assert lib.rnnt_greedy_decode_workspace_bytes(128, 1024, 1020, 512) == 0        # H % 8
+    assert lib.rnnt_greedy_decode_stack_workspace_bytes(128, 1024, 1024, 512, 4) == 0   # more than three layers
+    rc = lib.rnnt_greedy_decode_lstm(None, None, None, None, None, None, None, None, 4, 10, 29, 64, 64, 28, 2, None, 20,
+                                     None, None, 0, None)
+    assert rc == 1 and b"NULL" in lib.rnnt_last_error()
+    dummy = ctypes.c_void_p(16)   # never dereferenced: the range checks come first
+    rc = lib.rnnt_greedy_decode_lstm_stack(dummy, dummy, dummy, None, dummy, dummy, 1, None, None, dummy, None, 4, 10, 29,
+                                           64, 64, 29, 2, dummy, 20, dummy, dummy, 1 << 20, None)
+    assert rc == 1 and b"blank=29" in lib.rnnt_last_error()
+
+
 def test_product_path_fails_loudly_on_cpu_tensors():
     f = torch.zeros(1, 2, 8); g = torch.zeros(1, 3, 8); W = torch.zeros(5, 8)
     with pytest.raises(_lib.RNNTLibraryError, match="no CPU fallback"):
