@@ -26,6 +26,7 @@ thread_local char g_err[512] = "";
 int g_slab_tiles_override = 0;
 int g_path = 1;  // 1 = persistent kernels (persist.cu), 0 = per-slab kernels (joint.cu)
 int g_ring_slots = 2;
+int g_kg_override = 0;   // bring-up: K-groups of dW consumers in the backward mega-kernel (0 = plan's choice)
 int g_cluster = 2;      // forward kernel: CTAs per cluster; 4 = two CTA pairs sharing W through TMA multicast
                         // (measured slower: only 132 of the 148 SMs can host 4-clusters)
 int g_cluster_bwd = 2;  // backward mega-kernel: 4-clusters cannot all be co-resident (132 of 148 SMs), so pairs
@@ -125,7 +126,24 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
   p.o_hs = take(2 * static_cast<size_t>(kMaxPersistCtas) * 2 * kTileRows * H);
   // backward mega-kernel: role split of the 74 CTA pairs (see persist.cu)
   p.n_vt = (p.Vp + 255) / 256; p.n_ht = (H + 511) / 512; p.n_out = p.n_vt * p.n_ht;
-  p.KG = (2 * (kMaxPersistCtas / 2) / 3 + p.n_out) / (2 * p.n_out);  // round((n_pairs / 3) / n_out)
+  // Producer : consumer split of the 74 CTA pairs from a cycle model of one 256-row pair-tile (all MMAs are M = 256
+  // pair MMAs of ~128 cycles; epilogue costs per 256-column chunk measured with scripts/prof_mega_chunks.py).  A
+  // producer pair runs the dz and dh passes, MMAs overlapped with the epilogue of the previous chunk; the consumers of
+  // one K-group together add the pair-tile to every dW block.  V = H = 1024: 74 k vs 33 k cycles -> 24 consumer pairs
+  // (3 K-groups of 8 blocks); V = 29, H = 512 (epilogue-bound producers): 23 k vs 4 k -> 11 (measured optimum 11-13,
+  // scripts/kg_sweep.py; the flop-balanced 25 : 49 split it replaces ran configs[1] 14 % slower).
+  {
+    const double kb_h = (H + 63) / 64, kb_v = p.Vp / 64;
+    const double ch_v = (p.Vp + 255) / 256, ch_h = (H + 255) / 256;
+    const double mma_p = (ch_v * kb_h + ch_h * kb_v) * 4 * 128;
+    const double epi_p = 8000.0 * p.Vp / 256 + 10500.0 * H / 256;
+    const double prod = mma_p > epi_p ? mma_p : epi_p;
+    double cons = 0;   // per block: 4 k-blocks x (1 or 2 accumulators) x 4 MMAs
+    for (int hb = 0; hb < p.n_ht; ++hb) cons += p.n_vt * 4 * ((H - hb * 512 > 256) ? 8 : 4) * 128.0;
+    const double c_ideal = (kMaxPersistCtas / 2) * cons / (cons + prod);
+    p.KG = static_cast<int>(c_ideal / p.n_out + 0.5);
+  }
+  if (g_kg_override > 0) p.KG = g_kg_override;
   if (p.KG < 1) p.KG = 1;
   p.C = p.n_out * p.KG;
   p.P = kMaxPersistCtas / 2 - p.C;
@@ -348,6 +366,7 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "path")) g_path = value;
   if (!strcmp(key, "decode_cooperative")) set_decode_cooperative(value);
   if (!strcmp(key, "decode_prof")) g_decode_prof = value;
+  if (!strcmp(key, "mega_kg")) g_kg_override = value;
   if (!strcmp(key, "decode_variant") && (value == 0 || value == 1)) g_decode_variant = value;
   if (!strcmp(key, "decode_cluster") && value >= 1 && value <= 16) g_decode_cluster = value;
   if (!strcmp(key, "mega_cooperative")) set_bwd_mega_cooperative(value);  // 0: plain launch (ncu cannot replay cooperative launches)
