@@ -134,6 +134,20 @@ int rnnt_greedy_decode_lstm_stack(const void* f, const int32_t* lens, const void
                                   int V, int H, int Hp, int blank, int max_symbols, int32_t* sym, int sym_cap,
                                   int32_t* n_sym, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same loop for a GRU prediction network (torch.nn.GRU: r = s(W_ir x + b_ir + W_hr h + b_hr), z likewise,
+ * n = tanh(W_in x + b_in + r (W_hn h + b_hn)), h' = (1 - z) n + z h).  Arguments as for rnnt_greedy_decode_lstm_stack with
+ * FOUR rows per hidden unit in the order (r, z, n_hidden, n_input):
+ *   gate_table f32 [V+1][4*Hp]   (W_ir e_v + b_ir + b_hr | W_iz e_v + b_iz + b_hz | b_hn | W_in e_v + b_in)
+ *   W_hh       bf16 [4*Hp][Hp]   (W_hr | W_hz | W_hn | 0)
+ *   W_upper    bf16 [n-1][4*Hp][2*Hp]  rows ([W_ir|W_hr] | [W_iz|W_hz] | [0|W_hn] | [W_in|0]) of layer l
+ *   bias_upper f32  [n-1][4*Hp]        (b_ir + b_hr | b_iz + b_hz | b_hn | b_in)
+ * so that the data movement is the LSTM's; h is kept in fp32 for the blend and rounded to bf16 as a tensor-core operand. */
+int rnnt_greedy_decode_gru_stack(const void* f, const int32_t* lens, const void* W, const float* bias,
+                                 const float* gate_table, const void* W_hh, int n_layers, const void* W_upper,
+                                 const float* bias_upper, const void* W_proj, const float* bias_proj, int B, int Tmax,
+                                 int V, int H, int Hp, int blank, int max_symbols, int32_t* sym, int sym_cap,
+                                 int32_t* n_sym, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Debug / test hooks (not part of the drop-in surface). */
 int rnnt_debug_copy_stats(const void* workspace, int B, int Tmax, int Umax, int V, int H, float* lp_blank,
                           float* lp_label, float* c_blank, float* c_label, float* lnp_beta, void* stream);

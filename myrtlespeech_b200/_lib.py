@@ -30,6 +30,7 @@ SIGNATURES = {
     "rnnt_greedy_decode_lstm": (_c_int, [_vp] * 8 + [_c_int] * 7 + [_vp, _c_int, _vp, _vp, _c_size_t, _vp]),
     "rnnt_greedy_decode_stack_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "rnnt_greedy_decode_lstm_stack": (_c_int, [_vp] * 6 + [_c_int] + [_vp] * 4 + [_c_int] * 7 + [_vp, _c_int, _vp, _vp, _c_size_t, _vp]),
+    "rnnt_greedy_decode_gru_stack": (_c_int, [_vp] * 6 + [_c_int] + [_vp] * 4 + [_c_int] * 7 + [_vp, _c_int, _vp, _vp, _c_size_t, _vp]),
     "rnnt_debug_copy_stats": (_c_int, [_vp] + [_c_int] * 5 + [_vp] * 5 + [_vp]),
     "rnnt_debug_set": (None, [ctypes.c_char_p, _c_int]),
     "rnnt_debug_get": (ctypes.c_longlong, [ctypes.c_char_p]),

@@ -678,11 +678,35 @@ int rnnt_greedy_decode_lstm(const void* f, const int32_t* lens, const void* W, c
                                        H, Hp, blank, max_symbols, sym, sym_cap, n_sym, workspace, workspace_bytes, stream);
 }
 
+static int decode_stack_impl(int cell, const void* f, const int32_t* lens, const void* W, const float* bias,
+                             const float* gate_table, const void* W_hh, int n_layers, const void* W_upper,
+                             const float* bias_upper, const void* W_proj, const float* bias_proj, int B, int Tmax, int V,
+                             int H, int Hp, int blank, int max_symbols, int32_t* sym, int sym_cap, int32_t* n_sym,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 int rnnt_greedy_decode_lstm_stack(const void* f, const int32_t* lens, const void* W, const float* bias,
                                   const float* gate_table, const void* W_hh, int n_layers, const void* W_upper,
                                   const float* bias_upper, const void* W_proj, const float* bias_proj, int B, int Tmax, int V,
                                   int H, int Hp, int blank, int max_symbols, int32_t* sym, int sym_cap, int32_t* n_sym,
                                   void* workspace, size_t workspace_bytes, void* stream) {
+  return decode_stack_impl(0, f, lens, W, bias, gate_table, W_hh, n_layers, W_upper, bias_upper, W_proj, bias_proj, B, Tmax, V,
+                           H, Hp, blank, max_symbols, sym, sym_cap, n_sym, workspace, workspace_bytes, stream);
+}
+
+int rnnt_greedy_decode_gru_stack(const void* f, const int32_t* lens, const void* W, const float* bias,
+                                 const float* gate_table, const void* W_hh, int n_layers, const void* W_upper,
+                                 const float* bias_upper, const void* W_proj, const float* bias_proj, int B, int Tmax, int V,
+                                 int H, int Hp, int blank, int max_symbols, int32_t* sym, int sym_cap, int32_t* n_sym,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  return decode_stack_impl(1, f, lens, W, bias, gate_table, W_hh, n_layers, W_upper, bias_upper, W_proj, bias_proj, B, Tmax, V,
+                           H, Hp, blank, max_symbols, sym, sym_cap, n_sym, workspace, workspace_bytes, stream);
+}
+
+static int decode_stack_impl(int cell, const void* f, const int32_t* lens, const void* W, const float* bias,
+                             const float* gate_table, const void* W_hh, int n_layers, const void* W_upper,
+                             const float* bias_upper, const void* W_proj, const float* bias_proj, int B, int Tmax, int V,
+                             int H, int Hp, int blank, int max_symbols, int32_t* sym, int sym_cap, int32_t* n_sym,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   if (B < 1 || Tmax < 1 || V < 1 || sym_cap < 1 || max_symbols < 1 || n_layers < 1)
     return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d V=%d sym_cap=%d max_symbols=%d n_layers=%d out of range", B, Tmax, V,
                 sym_cap, max_symbols, n_layers);
@@ -693,7 +717,7 @@ int rnnt_greedy_decode_lstm_stack(const void* f, const int32_t* lens, const void
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const CDecPlan c = make_cdec_plan(B, V, H, Hp, g_decode_cluster, n_layers);
-  const bool want_cluster = g_decode_variant == 1 || n_layers > 1;   // the grid-barrier schedule is single-layer only
+  const bool want_cluster = g_decode_variant == 1 || n_layers > 1 || cell != 0;   // the grid-barrier schedule: one LSTM layer
   if (want_cluster && c.ok && workspace_bytes >= c.w_total && max_clusters_greedy_decode(c.smem, c.C) >= 1) {
     __nv_bfloat16* whh_perm = reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* wup_perm = reinterpret_cast<__nv_bfloat16*>(ws + c.w_wup);
@@ -717,7 +741,7 @@ int rnnt_greedy_decode_lstm_stack(const void* f, const int32_t* lens, const void
     a.B = B; a.Tmax = Tmax; a.V = V; a.H = H; a.Hp = Hp; a.blank = blank; a.S = max_symbols; a.sym_cap = sym_cap;
     a.max_steps = Tmax * max_symbols + 1;
     a.C = c.C; a.RJ = c.RJ; a.RP = c.RP; a.up = c.up; a.mtJ = c.mtJ; a.mtP = c.mtP; a.mtL = c.mtL; a.kbH = c.kbH; a.kbHp = c.kbHp;
-    a.n_stages = c.n_stages; a.tmem_cols = c.tmem_cols; a.NL = n_layers;
+    a.n_stages = c.n_stages; a.tmem_cols = c.tmem_cols; a.NL = n_layers; a.cell = cell;
     a.o_hj = c.o_hj; a.o_layers = c.o_layers; a.layer_stride = c.layer_stride; a.o_gates = c.o_gates;
     a.o_amax = c.o_amax; a.o_part = c.o_part; a.o_state = c.o_state; a.o_bars = c.o_bars;
     a.f = static_cast<const __nv_bfloat16*>(f); a.lens = lens; a.bias_j = bias; a.table = gate_table; a.bias_up = bias_upper;
@@ -729,9 +753,9 @@ int rnnt_greedy_decode_lstm_stack(const void* f, const int32_t* lens, const void
     CUDA_TRY(cudaGetLastError());
     return RNNT_OK;
   }
-  if (n_layers > 1)
-    return fail(RNNT_ERR_UNSUPPORTED, "fused greedy decode does not cover B=%d V=%d H=%d Hp=%d with %d LSTM layers", B, V, H, Hp,
-                n_layers);
+  if (n_layers > 1 || cell != 0)
+    return fail(RNNT_ERR_UNSUPPORTED, "fused greedy decode does not cover B=%d V=%d H=%d Hp=%d with %d %s layers", B, V, H, Hp,
+                n_layers, cell ? "GRU" : "LSTM");
   const DecPlan d = make_dec_plan(B, V, H, Hp);
   if (!d.ok) return fail(RNNT_ERR_UNSUPPORTED, "fused greedy decode does not cover B=%d V=%d H=%d Hp=%d", B, V, H, Hp);
   if (workspace_bytes < d.w_total)

@@ -704,7 +704,8 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
 #pragma unroll
           for (int i = 0; i < kNH; ++i) {
             const float x = raw[i] + tv[i];
-            a[i] = quad == 2 ? tanh_f(x) : sigmoid_f(x);
+            if (p.cell == 0) a[i] = quad == 2 ? tanh_f(x) : sigmoid_f(x);   // LSTM: i, f, g, o
+            else a[i] = quad < 2 ? sigmoid_f(x) : x;                        // GRU: r, z, hidden and input halves of n
           }
           float4* gdst = reinterpret_cast<float4*>(gates + ((m * 4 + quad) * 32 + lane) * kNB + n0);
           gdst[0] = make_float4(a[0], a[1], a[2], a[3]);
@@ -718,10 +719,17 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
           __nv_bfloat16 hv;
           if (s_lab[n] >= 0) {
             const float* gm = gates + (m * 4 * 32 + j) * kNB + n;
-            const float gi = gm[0], gf = gm[32 * kNB], gg = gm[2 * 32 * kNB], go = gm[3 * 32 * kNB];
-            const float c_new = gf * c_s[ul * kNB + n] + gi * gg;
-            c_s[ul * kNB + n] = c_new;
-            hv = __float2bfloat16_rn(go * tanh_f(c_new));
+            const float g0 = gm[0], g1 = gm[32 * kNB], g2 = gm[2 * 32 * kNB], g3 = gm[3 * 32 * kNB];
+            if (p.cell == 0) {   // LSTM: c' = f c + i g, h' = o tanh(c')
+              const float c_new = g1 * c_s[ul * kNB + n] + g0 * g2;
+              c_s[ul * kNB + n] = c_new;
+              hv = __float2bfloat16_rn(g3 * tanh_f(c_new));
+            } else {             // GRU: n = tanh(n_x + r n_h), h' = (1 - z) n + z h; c_s keeps h in fp32
+              const float nn = tanh_f(g3 + g0 * g2);
+              const float h_new = nn + g1 * (c_s[ul * kNB + n] - nn);
+              c_s[ul * kNB + n] = h_new;
+              hv = __float2bfloat16_rn(h_new);
+            }
             hown[ul * kNB + n] = hv;
           } else {
             hv = hown[ul * kNB + n];

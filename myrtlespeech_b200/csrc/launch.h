@@ -192,7 +192,8 @@ struct ClusterDecodeArgs {
   int mtJ, mtP, mtL;       // 128-row accumulator tiles per CTA and product
   int kbH, kbHp;           // k-blocks over H / Hp
   int n_stages, tmem_cols;
-  int NL;                  // LSTM layers of the prediction network (1..3)
+  int NL;                  // recurrent layers of the prediction network (1..3)
+  int cell;                // 0 = LSTM (gate rows i, f, g, o), 1 = GRU (gate rows r, z, n_hidden, n_input)
   int o_hj, o_layers, layer_stride, o_gates, o_amax, o_part, o_state, o_bars;
   const __nv_bfloat16* f;
   const int* lens;

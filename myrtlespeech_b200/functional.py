@@ -165,8 +165,10 @@ def greedy_decode_lstm_supported(B: int, V: int, H: int, Hp: int, n_layers: int 
 def greedy_decode_lstm(f: torch.Tensor, lens: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor],
                        gate_table: torch.Tensor, W_hh: torch.Tensor, W_proj: torch.Tensor,
                        bias_proj: Optional[torch.Tensor], blank: int, max_symbols: int,
-                       W_upper: Optional[torch.Tensor] = None, bias_upper: Optional[torch.Tensor] = None):
-    """Whole greedy decode of a batch in one launch (see ``rnnt_greedy_decode_lstm_stack`` in include/rnnt_b200.h).
+                       W_upper: Optional[torch.Tensor] = None, bias_upper: Optional[torch.Tensor] = None,
+                       cell: str = "lstm"):
+    """Whole greedy decode of a batch in one launch (see ``rnnt_greedy_decode_lstm_stack`` / ``rnnt_greedy_decode_gru_stack``
+    in include/rnnt_b200.h; ``cell="gru"`` expects the four-rows-per-unit GRU packing described there).
 
     f bf16 (B,T,H); lens int32 (B) on the device; W bf16 (V,H); gate_table fp32 (V+1, 4*Hp); W_hh bf16 (4*Hp, Hp);
     W_proj bf16 (H, Hp); for an n-layer LSTM ``W_upper`` bf16 (n-1, 4*Hp, 2*Hp) = [W_ih_l | W_hh_l] and ``bias_upper``
@@ -190,8 +192,11 @@ def greedy_decode_lstm(f: torch.Tensor, lens: torch.Tensor, W: torch.Tensor, bia
     cap = max(1, Tmax * max_symbols)
     sym = torch.zeros(B, cap, dtype=torch.int32, device=f.device)
     n_sym = torch.zeros(B, dtype=torch.int32, device=f.device)
-    _lib.check(lib.rnnt_greedy_decode_lstm_stack(_ptr(f), _ptr(lens), _ptr(W), _ptr(bias), _ptr(gate_table), _ptr(W_hh),
-                                                 n_layers, _ptr(W_upper), _ptr(bias_upper), _ptr(W_proj), _ptr(bias_proj),
-                                                 B, Tmax, V, H, Hp, int(blank), int(max_symbols), _ptr(sym), cap,
-                                                 _ptr(n_sym), _ptr(ws), nbytes, _stream()))
+    if cell not in ("lstm", "gru"):
+        raise ValueError(f"cell={cell!r} must be 'lstm' or 'gru'")
+    entry = lib.rnnt_greedy_decode_lstm_stack if cell == "lstm" else lib.rnnt_greedy_decode_gru_stack
+    _lib.check(entry(_ptr(f), _ptr(lens), _ptr(W), _ptr(bias), _ptr(gate_table), _ptr(W_hh),
+                     n_layers, _ptr(W_upper), _ptr(bias_upper), _ptr(W_proj), _ptr(bias_proj),
+                     B, Tmax, V, H, Hp, int(blank), int(max_symbols), _ptr(sym), cap,
+                     _ptr(n_sym), _ptr(ws), nbytes, _stream()))
     return sym, n_sym

@@ -72,7 +72,8 @@ class RNNTGreedyDecoder(torch.nn.Module):
             model.train(was_training)
 
     #: run the whole loop (LSTM cell + projection + joint argmax + bookkeeping) as ONE launch when the prediction network
-    #: is a single-layer LSTM (``rnnt_greedy_decode_lstm``); otherwise one CUDA graph per step
+    #: is an LSTM or GRU of up to three layers (``rnnt_greedy_decode_lstm_stack`` / ``_gru_stack``); otherwise one CUDA
+    #: graph per step
     USE_FUSED_LOOP = True
     #: decode steps enqueued between two host checks of "is any utterance still active"
     SYNC_EVERY = 32
@@ -99,9 +100,9 @@ class RNNTGreedyDecoder(torch.nn.Module):
         if self.USE_FUSED_LOOP and T > 0:
             packed = _pack_lstm_prediction(pred, B, Wb.size(0), H)
             if packed is not None:
-                table, whh, wproj, bproj, wup, bup = packed
+                table, whh, wproj, bproj, wup, bup, cell = packed
                 sym, n_sym = greedy_decode_lstm(fb, lens.contiguous(), Wb, bias, table, whh, wproj, bproj, blank, S,
-                                                W_upper=wup, bias_upper=bup)
+                                                W_upper=wup, bias_upper=bup, cell=cell)
                 sym_h, n_h = sym.cpu(), n_sym.cpu().tolist()
                 return [sym_h[b, : n_h[b]].tolist() for b in range(B)]
 
@@ -147,37 +148,63 @@ class RNNTGreedyDecoder(torch.nn.Module):
 
 
 def _pack_lstm_prediction(pred, B: int, V: int, H: int):
-    """``(gate_table, W_hh, W_proj, b_proj, W_upper, bias_upper)`` for the one-launch decode, or None if ``pred`` is not an
-    embedding + unidirectional LSTM of 1..3 layers + projection (``RNNTPredictionNet`` layout) the fused kernel covers.
+    """``(gate_table, W_hh, W_proj, b_proj, W_upper, bias_upper, cell)`` for the one-launch decode, or None if ``pred`` is
+    not an embedding + unidirectional LSTM / GRU of 1..3 layers + projection (``RNNTPredictionNet`` layout) the fused kernel
+    covers.
 
-    ``gate_table[v] = W_ih . emb[v] + b_ih + b_hh`` (fp32) folds the embedding lookup and the input half of the cell
-    into one row gather per emitted label; row ``vocab_size`` is the start-of-sequence input."""
+    LSTM: ``gate_table[v] = W_ih . emb[v] + b_ih + b_hh`` (fp32) folds the embedding lookup and the input half of the cell
+    into one row gather per emitted label; row ``vocab_size`` is the start-of-sequence input.  Upper layers are passed as
+    ``[W_ih_l | W_hh_l]`` with summed biases.  GRU: four rows per hidden unit -- r, z, the hidden half of n and the input
+    half of n -- so that the kernel moves the same data as for an LSTM (``rnnt_greedy_decode_gru_stack``)."""
     emb, rnn, proj = getattr(pred, "embedding", None), getattr(pred, "rnn", None), getattr(pred, "proj", None)
-    if not (isinstance(emb, torch.nn.Embedding) and isinstance(rnn, torch.nn.LSTM) and isinstance(proj, torch.nn.Linear)):
+    if not (isinstance(emb, torch.nn.Embedding) and isinstance(rnn, (torch.nn.LSTM, torch.nn.GRU))
+            and isinstance(proj, torch.nn.Linear)):
         return None
     if rnn.num_layers > 3 or rnn.bidirectional or getattr(rnn, "proj_size", 0) != 0:
         return None
     if emb.num_embeddings != V + 1 or proj.out_features != H or not emb.weight.is_cuda:
         return None
-    Hp = rnn.hidden_size
-    if not greedy_decode_lstm_supported(B, V, H, Hp, rnn.num_layers):
+    Hp, L = rnn.hidden_size, rnn.num_layers
+    if not greedy_decode_lstm_supported(B, V, H, Hp, L):
         return None
-    table = emb.weight.detach().float() @ rnn.weight_ih_l0.detach().float().t()
-    if rnn.bias:
-        table = table + (rnn.bias_ih_l0.detach().float() + rnn.bias_hh_l0.detach().float())
-    whh = rnn.weight_hh_l0.detach().to(torch.bfloat16).contiguous()
+    dev = emb.weight.device
+
+    def prm(name, l):
+        return getattr(rnn, f"{name}_l{l}").detach().float()
+
+    def bias(name, l):
+        return prm(name, l) if rnn.bias else torch.zeros(prm("weight_ih", l).size(0), device=dev)
+
     wproj = proj.weight.detach().to(torch.bfloat16).contiguous()
     bproj = None if proj.bias is None else proj.bias.detach().float().contiguous()
-    wup = bup = None
-    if rnn.num_layers > 1:   # upper layers: [W_ih_l | W_hh_l] side by side, summed biases
-        wup = torch.stack([torch.cat([getattr(rnn, f"weight_ih_l{l}").detach(), getattr(rnn, f"weight_hh_l{l}").detach()], 1)
-                           for l in range(1, rnn.num_layers)]).to(torch.bfloat16).contiguous()
-        if rnn.bias:
-            bup = torch.stack([getattr(rnn, f"bias_ih_l{l}").detach().float() + getattr(rnn, f"bias_hh_l{l}").detach().float()
-                               for l in range(1, rnn.num_layers)]).contiguous()
-        else:
-            bup = torch.zeros(rnn.num_layers - 1, 4 * Hp, device=wup.device)
-    return table.contiguous(), whh, wproj, bproj, wup, bup
+    e = emb.weight.detach().float()
+    if isinstance(rnn, torch.nn.LSTM):
+        table = e @ prm("weight_ih", 0).t() + (bias("bias_ih", 0) + bias("bias_hh", 0))
+        whh = prm("weight_hh", 0)
+        wup = [torch.cat([prm("weight_ih", l), prm("weight_hh", l)], 1) for l in range(1, L)]
+        bup = [bias("bias_ih", l) + bias("bias_hh", l) for l in range(1, L)]
+        cell = "lstm"
+    else:
+        def split(t):
+            return t[:Hp], t[Hp:2 * Hp], t[2 * Hp:]
+
+        w_ir, w_iz, w_in = split(prm("weight_ih", 0)); w_hr, w_hz, w_hn = split(prm("weight_hh", 0))
+        b_ir, b_iz, b_in = split(bias("bias_ih", 0)); b_hr, b_hz, b_hn = split(bias("bias_hh", 0))
+        table = torch.cat([e @ w_ir.t() + b_ir + b_hr, e @ w_iz.t() + b_iz + b_hz, b_hn.expand(e.size(0), Hp),
+                           e @ w_in.t() + b_in], 1)
+        whh = torch.cat([w_hr, w_hz, w_hn, torch.zeros_like(w_hn)], 0)
+        wup, bup = [], []
+        for l in range(1, L):
+            w_ir, w_iz, w_in = split(prm("weight_ih", l)); w_hr, w_hz, w_hn = split(prm("weight_hh", l))
+            b_ir, b_iz, b_in = split(bias("bias_ih", l)); b_hr, b_hz, b_hn = split(bias("bias_hh", l))
+            z = torch.zeros_like(w_hn)
+            wup.append(torch.cat([torch.cat([w_ir, w_hr], 1), torch.cat([w_iz, w_hz], 1), torch.cat([z, w_hn], 1),
+                                  torch.cat([w_in, z], 1)], 0))
+            bup.append(torch.cat([b_ir + b_hr, b_iz + b_hz, b_hn, b_in]))
+        cell = "gru"
+    wup_t = torch.stack(wup).to(torch.bfloat16).contiguous() if wup else None
+    bup_t = torch.stack(bup).contiguous() if bup else None
+    return table.contiguous(), whh.to(torch.bfloat16).contiguous(), wproj, bproj, wup_t, bup_t, cell
 
 
 def _clone_hidden(h):

@@ -395,3 +395,67 @@ def lstm_pred_step(
         return out, new_state
 
     return step
+
+
+def gru_pred_step(
+    emb: np.ndarray,
+    w_ih: Sequence[np.ndarray],
+    w_hh: Sequence[np.ndarray],
+    b_ih: Sequence[Optional[np.ndarray]],
+    b_hh: Sequence[Optional[np.ndarray]],
+    w_proj: np.ndarray,
+    b_proj: Optional[np.ndarray],
+    faithful: bool = False,
+) -> Callable[[Optional[int], object], Tuple[np.ndarray, object]]:
+    """As :func:`lstm_pred_step` for a stack of GRU layers (``torch.nn.GRU`` gate order r, z, n:
+    ``n = tanh(W_in x + b_in + r * (W_hn h + b_hn))``, ``h' = (1 - z) n + z h``).  ``faithful=True`` rounds where the
+    one-launch CUDA decode rounds: layer 0's input half is an fp32 table, every product sees bf16 ``h`` and bf16
+    weights with fp32 accumulation, the blend uses the fp32 ``h``, and the projected ``g`` is rounded to bf16."""
+    n_layers = len(w_ih)
+    emb = np.asarray(emb, dtype=np.float64)
+    w_ih = [np.asarray(w, dtype=np.float64) for w in w_ih]
+    w_hh = [np.asarray(w, dtype=np.float64) for w in w_hh]
+    w_proj = np.asarray(w_proj, dtype=np.float64)
+    hp = w_hh[0].shape[1]
+    z3 = np.zeros(3 * hp)
+    b_ih = [z3 if b is None else np.asarray(b, dtype=np.float64) for b in b_ih]
+    b_hh = [z3 if b is None else np.asarray(b, dtype=np.float64) for b in b_hh]
+    table = emb @ w_ih[0].T + b_ih[0]          # input half of layer 0 per label (b_hr, b_hz are added below)
+    if faithful:
+        r32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)  # noqa: E731
+        table[:, :2 * hp] = r32(table[:, :2 * hp] + b_hh[0][:2 * hp])
+        table[:, 2 * hp:] = r32(table[:, 2 * hp:])
+        b_hh = [np.concatenate([np.zeros(2 * hp), b[2 * hp:]]) if l == 0 else b for l, b in enumerate(b_hh)]
+        w_hh = [bf16_round(w) for w in w_hh]
+        w_ih = [w_ih[0]] + [bf16_round(w) for w in w_ih[1:]]
+        w_proj = bf16_round(w_proj)
+    bp = np.zeros(w_proj.shape[0]) if b_proj is None else np.asarray(b_proj, dtype=np.float64)
+    sos = emb.shape[0] - 1
+
+    def sigmoid(x):
+        return 1.0 / (1.0 + np.exp(-x))
+
+    def step(label: Optional[int], state):
+        if state is None:
+            state = [np.zeros(hp) for _ in range(n_layers)]
+        new_state = []
+        x = None
+        for l in range(n_layers):
+            h = state[l]
+            h_op = bf16_round(h) if faithful else h
+            gi = table[sos if label is None else int(label)] if l == 0 else w_ih[l] @ x + b_ih[l]
+            gh = w_hh[l] @ h_op + b_hh[l]
+            r = sigmoid(gi[:hp] + gh[:hp])
+            z = sigmoid(gi[hp:2 * hp] + gh[hp:2 * hp])
+            n = np.tanh(gi[2 * hp:] + r * gh[2 * hp:])
+            h = n + z * (h - n)
+            if faithful:
+                h = h.astype(np.float32).astype(np.float64)
+            new_state.append(h)
+            x = bf16_round(h) if faithful else h
+        out = w_proj @ x + bp
+        if faithful:
+            out = bf16_round(out)
+        return out, new_state
+
+    return step

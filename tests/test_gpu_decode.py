@@ -99,11 +99,11 @@ def test_greedy_decoder_constructed_path():
 # --------------------------------------------------------------------------------------------------------------------
 # one-launch decode: LSTM prediction cell + projection + joint argmax + bookkeeping looped on the device
 # --------------------------------------------------------------------------------------------------------------------
-def _lstm_case(seed, B, T, V, H, Hp, E, lens=None, blank_bias=2.5, n_layers=1):
+def _lstm_case(seed, B, T, V, H, Hp, E, lens=None, blank_bias=2.5, n_layers=1, rnn_type="lstm"):
     """Seeded model + inputs (CPU generator, so the GPU box and the CPU container see the same numbers)."""
     torch.manual_seed(seed)
     joint = RNNTJoint(H, V)
-    pred = RNNTPredictionNet(V, E, Hp, n_layers, H)
+    pred = RNNTPredictionNet(V, E, Hp, n_layers, H, rnn_type=rnn_type)
     with torch.no_grad():
         joint.fc.weight.mul_(4.0)   # spread the logits so that argmax margins are far above bf16 noise
         pred.proj.weight.mul_(3.0)
@@ -120,10 +120,10 @@ def _lstm_case(seed, B, T, V, H, Hp, E, lens=None, blank_bias=2.5, n_layers=1):
 def _oracle_transcripts(joint, pred, f, lens, blank, S):
     n = lambda t: None if t is None else t.detach().cpu().float().numpy()  # noqa: E731
     r, L = pred.rnn, range(pred.rnn.num_layers)
-    step = O.lstm_pred_step(n(pred.embedding.weight), [n(getattr(r, f"weight_ih_l{l}")) for l in L],
-                            [n(getattr(r, f"weight_hh_l{l}")) for l in L], [n(getattr(r, f"bias_ih_l{l}")) for l in L],
-                            [n(getattr(r, f"bias_hh_l{l}")) for l in L], n(pred.proj.weight), n(pred.proj.bias),
-                            faithful=True)
+    make_step = O.lstm_pred_step if isinstance(r, torch.nn.LSTM) else O.gru_pred_step
+    step = make_step(n(pred.embedding.weight), [n(getattr(r, f"weight_ih_l{l}")) for l in L],
+                     [n(getattr(r, f"weight_hh_l{l}")) for l in L], [n(getattr(r, f"bias_ih_l{l}")) for l in L],
+                     [n(getattr(r, f"bias_hh_l{l}")) for l in L], n(pred.proj.weight), n(pred.proj.bias), faithful=True)
     return O.greedy_decode(f.float().numpy(), lens.numpy(), n(joint.fc.weight), n(joint.fc.bias), step, blank, S,
                            faithful=True, per_utterance_margin=True)
 
@@ -204,17 +204,20 @@ def test_fused_lstm_decode_at_configs4_widths(decode_variant):
 
 
 STACK_CASES = [
-    # seed, B, T, V, H, Hp, E, S, layers
-    (7, 5, 19, 40, 64, 64, 32, 2, 2),
-    (7, 20, 11, 300, 192, 200, 24, 3, 2),   # two clusters, Hp not a multiple of 64: padded k-block halves
-    (6, 6, 13, 29, 128, 72, 16, 2, 3),
+    # seed, B, T, V, H, Hp, E, S, layers, cell
+    (7, 5, 19, 40, 64, 64, 32, 2, 2, "lstm"),
+    (7, 20, 11, 300, 192, 200, 24, 3, 2, "lstm"),   # two clusters, Hp not a multiple of 64: padded k-block halves
+    (6, 6, 13, 29, 128, 72, 16, 2, 3, "lstm"),
+    (5, 5, 19, 40, 64, 64, 32, 2, 1, "gru"),
+    (2, 20, 11, 300, 192, 200, 24, 3, 2, "gru"),
+    (5, 6, 13, 29, 128, 72, 16, 2, 3, "gru"),
 ]
 
 
-@pytest.mark.parametrize("seed,B,T,V,H,Hp,E,S,layers", STACK_CASES)
-def test_fused_stacked_lstm_decode_matches_oracle(seed, B, T, V, H, Hp, E, S, layers):
-    """Prediction networks with 2 and 3 LSTM layers through the one-launch cluster kernel."""
-    joint, pred, f, lens = _lstm_case(seed, B, T, V, H, Hp, E, n_layers=layers)
+@pytest.mark.parametrize("seed,B,T,V,H,Hp,E,S,layers,cell", STACK_CASES)
+def test_fused_stacked_lstm_decode_matches_oracle(seed, B, T, V, H, Hp, E, S, layers, cell):
+    """LSTM stacks of 2 and 3 layers and GRU prediction networks through the one-launch cluster kernel."""
+    joint, pred, f, lens = _lstm_case(seed, B, T, V, H, Hp, E, n_layers=layers, rnn_type=cell)
     blank = V - 1
     want, margins = _oracle_transcripts(joint, pred, f, lens, blank, S)
     clear = [m > MARGIN for m in margins]

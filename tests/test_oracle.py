@@ -209,3 +209,22 @@ def test_lstm_pred_step_two_layers_matches_torch_lstm():
         got, state = step(lab, state)
         want, hx = pred.step(None if lab is None else torch.tensor([lab]), hx, 1, torch.device("cpu"))
         np.testing.assert_allclose(got, want[0].detach().numpy(), rtol=1e-10, atol=1e-12)
+
+
+def test_gru_pred_step_matches_torch_gru():
+    import torch
+    from myrtlespeech_b200.model.rnn_t import RNNTPredictionNet
+
+    torch.manual_seed(2)
+    V, E, Hp, H = 9, 5, 8, 6
+    pred = RNNTPredictionNet(V, E, Hp, 2, H, rnn_type="gru").cpu().double()
+    n = lambda t: t.detach().numpy()  # noqa: E731
+    r = pred.rnn
+    step = O.gru_pred_step(n(pred.embedding.weight), [n(r.weight_ih_l0), n(r.weight_ih_l1)],
+                           [n(r.weight_hh_l0), n(r.weight_hh_l1)], [n(r.bias_ih_l0), n(r.bias_ih_l1)],
+                           [n(r.bias_hh_l0), n(r.bias_hh_l1)], n(pred.proj.weight), n(pred.proj.bias))
+    state, hx = None, None
+    for lab in [None, 2, 8, 0, 0, 5]:
+        got, state = step(lab, state)
+        want, hx = pred.step(None if lab is None else torch.tensor([lab]), hx, 1, torch.device("cpu"))
+        np.testing.assert_allclose(got, want[0].detach().numpy(), rtol=1e-10, atol=1e-12)
