@@ -350,6 +350,7 @@ CDecPlan make_cdec_plan(int B, int V, int H, int Hp, int C, int NL = 1) {
 int g_decode_variant = 1;  // 1: one cluster per 16 utterances (default); 0: N-split over the grid with grid barriers
 int g_decode_cluster = 8;
 int g_decode_prof = 0;
+int g_decode_res = 1;    // keep the projection weights resident in TMEM when they fit
 
 }  // namespace
 
@@ -366,6 +367,7 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "path")) g_path = value;
   if (!strcmp(key, "decode_cooperative")) set_decode_cooperative(value);
   if (!strcmp(key, "decode_prof")) g_decode_prof = value;
+  if (!strcmp(key, "decode_resident")) g_decode_res = value;
   if (!strcmp(key, "mega_kg")) g_kg_override = value;
   if (!strcmp(key, "decode_variant") && (value == 0 || value == 1)) g_decode_variant = value;
   if (!strcmp(key, "decode_cluster") && value >= 1 && value <= 16) g_decode_cluster = value;
@@ -747,6 +749,20 @@ static int decode_stack_impl(int cell, const void* f, const int32_t* lens, const
     a.f = static_cast<const __nv_bfloat16*>(f); a.lens = lens; a.bias_j = bias; a.table = gate_table; a.bias_up = bias_upper;
     a.bias_p = bias_proj;
     a.sym = sym; a.n_sym = n_sym; a.prof = g_decode_prof;
+    {
+      // spare TMEM columns hold this CTA's W_proj rows (one 128-row tile, 32 columns per k-block) for the whole decode
+      const int acc_cols = 32 * (n_layers * c.mtL + c.mtP + c.mtJ);
+      a.res_p = g_decode_res && c.mtP == 1 && acc_cols + 32 * c.kbHp <= 512;
+      a.res_col = acc_cols;
+      a.w_proj = static_cast<const __nv_bfloat16*>(W_proj);
+      // ... and what is left holds the leading k-blocks of the first vocabulary tile (the product every step waits for)
+      a.res_j_col = acc_cols + (a.res_p ? 32 * c.kbHp : 0);
+      a.res_j = g_decode_res ? (512 - a.res_j_col) / 32 : 0;
+      if (a.res_j > c.kbH) a.res_j = c.kbH;
+      if (a.res_j < 0) a.res_j = 0;
+      a.w_joint = static_cast<const __nv_bfloat16*>(W);
+      if (a.res_p || a.res_j) a.tmem_cols = 512;
+    }
     cudaError_t e = cudaSuccess;
     KLAUNCH(K_MISC, s, e = launch_greedy_decode_cluster(tm_wj, tm_wl, tm_wu, tm_wp, a, (B + 15) / 16, c.smem, s));
     if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(RNNT_ERR_CUDA, "greedy decode (cluster) launch -> %s", cudaGetErrorString(e)); }

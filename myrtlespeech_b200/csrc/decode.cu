@@ -451,6 +451,7 @@ constexpr int kMma2Warp = 10;
 constexpr int kEpiThreads = 256;
 constexpr int kMaxTiles = 10;         // accumulator tiles (L of every layer + P + J) per CTA
 constexpr int kMaxLayers = 3;         // LSTM layers of the prediction network
+constexpr int kMaxLTiles = 4;         // gate tiles per layer and CTA (32 hidden units each)
 constexpr int kTileCols = 2 * kNB;    // TMEM columns per accumulator tile: one partial accumulator per issuing warp.
                                       // (Spreading one warp's MMAs over four accumulators was measured: no change --
                                       // the cost per MMA is issue latency of the thread, not an accumulator dependency.)
@@ -503,7 +504,8 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
   uint64_t* amaxfull_bar = hjfull_bar + 1;
   uint64_t* step_bar = amaxfull_bar + 1;
   uint64_t* fin_bar = step_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fin_bar + 1);
+  uint64_t* res_bar = fin_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -517,6 +519,7 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
     for (int i = 0; i < kMaxTiles; ++i) mbar_init(&tfull_bar[i], 2);   // one arrival per issuing warp
     for (int i = 0; i < 2 * kMaxLayers; ++i) mbar_init(&hfull_bar[i], 1);
     mbar_init(hjfull_bar, 1); mbar_init(amaxfull_bar, 1); mbar_init(step_bar, 1); mbar_init(fin_bar, 2);
+    mbar_init(res_bar, 128);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -545,8 +548,8 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       uint32_t it = 0;
       const bool prof = p.prof && blockIdx.x == 0;
       long long w_empty = 0, w_step = 0;
-      auto push = [&](const CUtensorMap* tm, int row0, int kb) {   // columns k * 64: the upper layers' [W_ih | W_hh] rows too
-        for (int k = 0; k < kb; ++k, ++it) {
+      auto push = [&](const CUtensorMap* tm, int row0, int kb, int k0 = 0) {   // k-blocks [k0, kb) of one 128-row tile
+        for (int k = k0; k < kb; ++k, ++it) {
           const int st = it % p.n_stages;
           const long long t0 = prof ? clock64() : 0;
           mbar_wait(&empty_bar[st], ((it / p.n_stages) & 1) ^ 1);
@@ -564,9 +567,10 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
         if (prof) w_step += clock64() - t0;
         for (int l = 1; l < NL; ++l)
           for (int m = 0; m < p.mtL; ++m) push(&tm_wu, ((l - 1) * C + static_cast<int>(rank)) * 4 * p.up + m * kBM, 2 * p.kbHp);
-        for (int m = 0; m < p.mtP; ++m) push(&tm_wp, static_cast<int>(rank) * p.RP + m * kBM, p.kbHp);
+        if (!p.res_p)
+          for (int m = 0; m < p.mtP; ++m) push(&tm_wp, static_cast<int>(rank) * p.RP + m * kBM, p.kbHp);
         push_l(0);
-        for (int m = 0; m < p.mtJ; ++m) push(&tm_wj, static_cast<int>(rank) * p.RJ + m * kBM, p.kbH);
+        for (int m = 0; m < p.mtJ; ++m) push(&tm_wj, static_cast<int>(rank) * p.RJ + m * kBM, p.kbH, m == 0 ? p.res_j : 0);
         for (int m = 1; m < p.mtL; ++m) push_l(m);
       }
       if (prof) { g_dec_prof[10] = w_empty; g_dec_prof[11] = w_step; }
@@ -591,12 +595,23 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
     uint64_t ad = ad0;
     // One accumulator tile over kb + kb1 k-blocks: the first kb against activation buffer b_base, the rest against b_base1
     // (upper LSTM layers: h of the layer below, then the layer's own previous h).
-    auto tile = [&](uint32_t b_base, int kb0, int slot, uint32_t b_base1 = 0, int kb1 = 0) {
+    auto tile = [&](uint32_t b_base, int kb0, int slot, uint32_t b_base1 = 0, int kb1 = 0, int res_k = 0, int res_col = 0) {
       const uint64_t bd0 = make_smem_desc_sw128(b_base, 16, 1024);
       const uint64_t bd1 = make_smem_desc_sw128(b_base1, 16, 1024) - static_cast<uint64_t>(kb0) * (kKBlk >> 4);
       const uint32_t d_tmem = tmem + slot * kTileCols + w * kNB, tf = smem_u32(&tfull_bar[slot]);
       const int kb = kb0 + kb1;
-      for (int k = 0; k < kb; ++k) {
+      if (res_k > 0) {   // leading k-blocks whose weights are resident in TMEM: A operand from TMEM, no ring slot
+        if (elect_one()) {
+          for (int k = w; k < res_k; k += 2) {
+            const uint64_t bd = bd0 + static_cast<uint64_t>(k) * (kKBlk >> 4);
+#pragma unroll
+            for (int kk = 0; kk < kBK / 16; ++kk)
+              umma_bf16_ts(d_tmem, tmem + res_col + (k * 4 + kk) * 8, bd + 2 * kk, idesc, (k > w || kk != 0) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      }
+      for (int k = res_k; k < kb; ++k) {
         if ((k & 1) == w) {
           {
             const long long t0 = prof ? clock64() : 0;   // try_wait itself suspends the warp: time the whole wait
@@ -621,10 +636,27 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       if (elect_one()) umma_commit_addr(tf);   // this warp's share of the tile (possibly empty when kb == 1) is issued
       __syncwarp();
     };
+    // The projection tile with its weights resident in TMEM (A operand from TMEM: no ring slot, no weight bytes).
+    auto tile_res = [&](uint32_t b_base, int kb, int slot) {
+      const uint64_t bd0 = make_smem_desc_sw128(b_base, 16, 1024);
+      const uint32_t d_tmem = tmem + slot * kTileCols + w * kNB, tf = smem_u32(&tfull_bar[slot]);
+      if (elect_one()) {
+        for (int k = w; k < kb; k += 2) {
+          const uint64_t bd = bd0 + static_cast<uint64_t>(k) * (kKBlk >> 4);
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk)
+            umma_bf16_ts(d_tmem, tmem + p.res_col + (k * 4 + kk) * 8, bd + 2 * kk, idesc, (k > w || kk != 0) ? 1u : 0u);
+        }
+        umma_commit_addr(tf);
+      }
+      __syncwarp();
+    };
+    if (p.res_p || p.res_j) { mbar_wait(res_bar, 0); tc_fence_after(); }
     // W_hh . h(s) -- the product of step s+1's cell -- needs h(s) but not the label emitted at step s (only its epilogue
     // does), so it is issued speculatively inside step s, in the two gaps in which these warps would otherwise wait for an
     // exchange: tile 0 while the hj slices travel, the other tiles while the argmax keys travel.
-    for (int m = 0; m < p.mtL; ++m) tile(smem_u32(hbuf(0, 0)), p.kbHp, m);   // step 0: h(-1) = 0
+    for (int m = 0; m < p.mtL; ++m)   // step 0: h(-1) = 0
+      tile(smem_u32(hbuf(0, 0)), p.kbHp, m);
     for (int s = 0; s <= p.max_steps; ++s) {
       const int cur = s & 1, nxt = cur ^ 1;
       const uint32_t hpar = (s >> 1) & 1;   // every h buffer is refilled every other step
@@ -639,13 +671,14 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       mbar_wait(&hfull_bar[2 * (NL - 1) + nxt], hpar);
       if (prof) w_dep += clock64() - t0;
       tc_fence_after();
-      for (int m = 0; m < p.mtP; ++m) tile(smem_u32(hbuf(NL - 1, nxt)), p.kbHp, slotP0 + m);
+      if (p.res_p) tile_res(smem_u32(hbuf(NL - 1, nxt)), p.kbHp, slotP0);
+      else for (int m = 0; m < p.mtP; ++m) tile(smem_u32(hbuf(NL - 1, nxt)), p.kbHp, slotP0 + m);
       tile(smem_u32(hbuf(0, nxt)), p.kbHp, 0);
       t0 = prof ? clock64() : 0;
       mbar_wait(hjfull_bar, s & 1);
       if (prof) w_dep += clock64() - t0;
       tc_fence_after();
-      for (int m = 0; m < p.mtJ; ++m) tile(smem_u32(hj), p.kbH, slotJ0 + m);
+      for (int m = 0; m < p.mtJ; ++m) tile(smem_u32(hj), p.kbH, slotJ0 + m, 0, 0, m == 0 ? p.res_j : 0, p.res_j_col);
       for (int m = 1; m < p.mtL; ++m) tile(smem_u32(hbuf(0, nxt)), p.kbHp, m);
     }
     if (prof) { g_dec_prof[12] = w_full; g_dec_prof[13] = w_dep; }
@@ -667,6 +700,36 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
     const uint32_t slice_h = static_cast<uint32_t>(p.up / 64) * kKBlk;
     const uint32_t slice_p = static_cast<uint32_t>(p.RP / 64) * kKBlk;
 
+    if ((p.res_p || p.res_j) && et < 128) {
+      // Weights that stay in TMEM for the whole decode: lane = output row, column c holds the bf16 pair (k = 2c, 2c + 1),
+      // 8 columns per K = 16 MMA.  Rows beyond the matrix and columns beyond K are zero.
+      auto load_rows = [&](const __nv_bfloat16* wr, bool row_ok, int K, int n_kb, int col0) {
+        for (int c = 0; c < n_kb * 4; ++c) {   // 16 K-elements = 8 columns per store
+          uint32_t v[8];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int k0 = c * 16 + q * 8;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (row_ok && k0 < K) x = __ldg(reinterpret_cast<const uint4*>(wr + k0));   // K % 8 == 0
+            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+          }
+          tmem_st8(tmem + (static_cast<uint32_t>(quad * 32) << 16) + col0 + c * 8, v);
+        }
+      };
+      if (p.res_p) {   // this CTA's rows of W_proj (one tile)
+        const int n_row = static_cast<int>(rank) * p.RP + row;
+        const bool row_ok = row < p.RP && n_row < p.H;
+        load_rows(p.w_proj + static_cast<size_t>(row_ok ? n_row : 0) * p.Hp, row_ok, p.Hp, p.kbHp, p.res_col);
+      }
+      if (p.res_j) {   // the first res_j k-blocks of this CTA's first vocabulary tile (on the critical path of every step)
+        const int v_row = static_cast<int>(rank) * p.RJ + row;
+        const bool row_ok = row < p.RJ && v_row < p.V;
+        load_rows(p.w_joint + static_cast<size_t>(row_ok ? v_row : 0) * p.H, row_ok, p.H, p.res_j, p.res_j_col);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(res_bar);
+    }
     const bool prof = p.prof && blockIdx.x == 0 && et == 0;
     long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long last = clock64();
@@ -680,21 +743,30 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
         float* c_s = cbuf(l);
         __nv_bfloat16* hown = hownbuf(l);
         uint8_t* hdst = hbuf(l, nxt);
-        for (int m = 0; m < p.mtL; ++m) {
-          const int u = static_cast<int>(rank) * p.up + m * 32 + lane;   // this thread: gate `quad` of unit u
-          float tv[kNH];
-          if (l == 0) {   // embedding + input half of the cell: one table row per emitted label
+        // input half of every gate tile of this layer, fetched before the first accumulator is waited for
+        float tva[kMaxLTiles][kNH];
 #pragma unroll
-            for (int i = 0; i < kNH; ++i) {
-              const int lab = s_lab[n0 + i];
-              tv[i] = (lab >= 0 && u < p.Hp) ? __ldg(p.table + static_cast<size_t>(lab) * gate_pitch + quad * p.Hp + u) : 0.0f;
+        for (int m = 0; m < kMaxLTiles; ++m) {
+          if (m < p.mtL) {
+            const int u = static_cast<int>(rank) * p.up + m * 32 + lane;   // this thread: gate `quad` of unit u
+            if (l == 0) {   // embedding + input half of the cell: one table row per emitted label
+#pragma unroll
+              for (int i = 0; i < kNH; ++i) {
+                const int lab = s_lab[n0 + i];
+                tva[m][i] = (lab >= 0 && u < p.Hp) ? __ldg(p.table + static_cast<size_t>(lab) * gate_pitch + quad * p.Hp + u) : 0.0f;
+              }
+            } else {
+              const float bu = u < p.Hp ? __ldg(p.bias_up + static_cast<size_t>(l - 1) * gate_pitch + quad * p.Hp + u) : 0.0f;
+#pragma unroll
+              for (int i = 0; i < kNH; ++i) tva[m][i] = bu;
             }
-          } else {
-            const float bu = u < p.Hp ? __ldg(p.bias_up + static_cast<size_t>(l - 1) * gate_pitch + quad * p.Hp + u) : 0.0f;
-#pragma unroll
-            for (int i = 0; i < kNH; ++i) tv[i] = bu;
           }
-          if (l == 0 && m == 0) DSTAMP(0);   // table gather issued
+        }
+        if (l == 0) DSTAMP(0);   // table gather issued
+#pragma unroll
+        for (int m = 0; m < kMaxLTiles; ++m) {
+          if (m >= p.mtL) break;
+          const float (&tv)[kNH] = tva[m];
           mbar_wait(&tfull_bar[l * p.mtL + m], par);
           if (l == 0 && m == 0) DSTAMP(1);   // waited for the L accumulator
           tc_fence_after();
@@ -739,13 +811,12 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
         }
         fence_proxy_async_smem();
         named_bar_sync(1, kEpiThreads);   // also: nobody still reads `gates` when the next layer overwrites it
-        if (et == 0) {
+        {   // one bulk copy per peer, issued by C - 1 different threads; the own barrier expects the peers' slices
           uint64_t* hf = &hfull_bar[2 * l + nxt];
-          mbar_arrive_expect_tx(hf, static_cast<uint32_t>(C - 1) * slice_h);
-          const uint32_t src = smem_u32(hdst) + rank * slice_h, bar = smem_u32(hf);
-          for (int d = 1; d < C; ++d) {
-            const uint32_t dst = (rank + d) % C;
-            bulk_copy_to_cluster(mapa_u32(src, dst), src, slice_h, mapa_u32(bar, dst));
+          if (et == 0) mbar_arrive_expect_tx(hf, static_cast<uint32_t>(C - 1) * slice_h);
+          if (et >= 32 && et < 31 + C) {
+            const uint32_t src = smem_u32(hdst) + rank * slice_h, dst = (rank + (et - 31)) % C;
+            bulk_copy_to_cluster(mapa_u32(src, dst), src, slice_h, mapa_u32(smem_u32(hf), dst));
           }
         }
       }
@@ -781,13 +852,10 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       tc_fence_before();
       fence_proxy_async_smem();
       named_bar_sync(1, kEpiThreads);
-      if (et == 0) {
-        mbar_arrive_expect_tx(hjfull_bar, static_cast<uint32_t>(C - 1) * slice_p);
-        const uint32_t src = smem_u32(hj) + rank * slice_p, bar = smem_u32(hjfull_bar);
-        for (int d = 1; d < C; ++d) {
-          const uint32_t dst = (rank + d) % C;
-          bulk_copy_to_cluster(mapa_u32(src, dst), src, slice_p, mapa_u32(bar, dst));
-        }
+      if (et == 0) mbar_arrive_expect_tx(hjfull_bar, static_cast<uint32_t>(C - 1) * slice_p);
+      if (et >= 32 && et < 31 + C) {
+        const uint32_t src = smem_u32(hj) + rank * slice_p, dst = (rank + (et - 31)) % C;
+        bulk_copy_to_cluster(mapa_u32(src, dst), src, slice_p, mapa_u32(smem_u32(hjfull_bar), dst));
       }
       DSTAMP(4);  // P epilogue + push issued
       // ---------------------------------------------------------------- J: logits -> argmax

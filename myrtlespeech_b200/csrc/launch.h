@@ -203,6 +203,11 @@ struct ClusterDecodeArgs {
   const float* bias_p;
   int* sym;
   int* n_sym;
+  int res_p;               // != 0: this CTA's W_proj rows live in TMEM columns [res_col, res_col + 32 kbHp) for the whole decode
+  int res_col;
+  int res_j, res_j_col;    // leading k-blocks of the first vocabulary tile resident in TMEM columns [res_j_col, + 32 res_j)
+  const __nv_bfloat16* w_proj;    // [H][Hp] (only read when res_p)
+  const __nv_bfloat16* w_joint;   // [V][H]  (only read when res_j)
   int prof;                // != 0: cluster 0 / rank 0 sums clock64 cycles per epilogue stage into g_dec_prof
 };
 int read_decode_prof(unsigned long long* out, int n);
