@@ -750,16 +750,18 @@ static int decode_stack_impl(int cell, const void* f, const int32_t* lens, const
     a.bias_p = bias_proj;
     a.sym = sym; a.n_sym = n_sym; a.prof = g_decode_prof;
     {
-      // spare TMEM columns hold this CTA's W_proj rows (one 128-row tile, 32 columns per k-block) for the whole decode
+      // Spare TMEM columns hold weights for the whole decode (32 columns per 64-wide k-block of a 128-row tile; A operand
+      // of the TS-form MMA): first the projection tile, then leading k-blocks of the first vocabulary tile.  (Measured
+      // the other way round -- 8 k-blocks of W, 4 of W_p, so that the streamed rest of W fits the ring: 23.7 -> 25.7 ms
+      // at warm clocks; the projection sits right behind the h exchange and gains more from needing no weights at all.)
       const int acc_cols = 32 * (n_layers * c.mtL + c.mtP + c.mtJ);
-      a.res_p = g_decode_res && c.mtP == 1 && acc_cols + 32 * c.kbHp <= 512;
+      int budget = g_decode_res ? (512 - acc_cols) / 32 : 0;
+      if (budget < 0) budget = 0;
+      a.res_p = c.mtP == 1 ? (budget < c.kbHp ? budget : c.kbHp) : 0;
+      a.res_j = budget - a.res_p < c.kbH ? budget - a.res_p : c.kbH;
       a.res_col = acc_cols;
+      a.res_j_col = acc_cols + 32 * a.res_p;
       a.w_proj = static_cast<const __nv_bfloat16*>(W_proj);
-      // ... and what is left holds the leading k-blocks of the first vocabulary tile (the product every step waits for)
-      a.res_j_col = acc_cols + (a.res_p ? 32 * c.kbHp : 0);
-      a.res_j = g_decode_res ? (512 - a.res_j_col) / 32 : 0;
-      if (a.res_j > c.kbH) a.res_j = c.kbH;
-      if (a.res_j < 0) a.res_j = 0;
       a.w_joint = static_cast<const __nv_bfloat16*>(W);
       if (a.res_p || a.res_j) a.tmem_cols = 512;
     }

@@ -567,8 +567,7 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
         if (prof) w_step += clock64() - t0;
         for (int l = 1; l < NL; ++l)
           for (int m = 0; m < p.mtL; ++m) push(&tm_wu, ((l - 1) * C + static_cast<int>(rank)) * 4 * p.up + m * kBM, 2 * p.kbHp);
-        if (!p.res_p)
-          for (int m = 0; m < p.mtP; ++m) push(&tm_wp, static_cast<int>(rank) * p.RP + m * kBM, p.kbHp);
+        for (int m = 0; m < p.mtP; ++m) push(&tm_wp, static_cast<int>(rank) * p.RP + m * kBM, p.kbHp, m == 0 ? p.res_p : 0);
         push_l(0);
         for (int m = 0; m < p.mtJ; ++m) push(&tm_wj, static_cast<int>(rank) * p.RJ + m * kBM, p.kbH, m == 0 ? p.res_j : 0);
         for (int m = 1; m < p.mtL; ++m) push_l(m);
@@ -636,21 +635,6 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       if (elect_one()) umma_commit_addr(tf);   // this warp's share of the tile (possibly empty when kb == 1) is issued
       __syncwarp();
     };
-    // The projection tile with its weights resident in TMEM (A operand from TMEM: no ring slot, no weight bytes).
-    auto tile_res = [&](uint32_t b_base, int kb, int slot) {
-      const uint64_t bd0 = make_smem_desc_sw128(b_base, 16, 1024);
-      const uint32_t d_tmem = tmem + slot * kTileCols + w * kNB, tf = smem_u32(&tfull_bar[slot]);
-      if (elect_one()) {
-        for (int k = w; k < kb; k += 2) {
-          const uint64_t bd = bd0 + static_cast<uint64_t>(k) * (kKBlk >> 4);
-#pragma unroll
-          for (int kk = 0; kk < kBK / 16; ++kk)
-            umma_bf16_ts(d_tmem, tmem + p.res_col + (k * 4 + kk) * 8, bd + 2 * kk, idesc, (k > w || kk != 0) ? 1u : 0u);
-        }
-        umma_commit_addr(tf);
-      }
-      __syncwarp();
-    };
     if (p.res_p || p.res_j) { mbar_wait(res_bar, 0); tc_fence_after(); }
     // W_hh . h(s) -- the product of step s+1's cell -- needs h(s) but not the label emitted at step s (only its epilogue
     // does), so it is issued speculatively inside step s, in the two gaps in which these warps would otherwise wait for an
@@ -671,8 +655,8 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       mbar_wait(&hfull_bar[2 * (NL - 1) + nxt], hpar);
       if (prof) w_dep += clock64() - t0;
       tc_fence_after();
-      if (p.res_p) tile_res(smem_u32(hbuf(NL - 1, nxt)), p.kbHp, slotP0);
-      else for (int m = 0; m < p.mtP; ++m) tile(smem_u32(hbuf(NL - 1, nxt)), p.kbHp, slotP0 + m);
+      for (int m = 0; m < p.mtP; ++m)
+        tile(smem_u32(hbuf(NL - 1, nxt)), p.kbHp, slotP0 + m, 0, 0, m == 0 ? p.res_p : 0, p.res_col);
       tile(smem_u32(hbuf(0, nxt)), p.kbHp, 0);
       t0 = prof ? clock64() : 0;
       mbar_wait(hjfull_bar, s & 1);
@@ -716,10 +700,10 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
           tmem_st8(tmem + (static_cast<uint32_t>(quad * 32) << 16) + col0 + c * 8, v);
         }
       };
-      if (p.res_p) {   // this CTA's rows of W_proj (one tile)
+      if (p.res_p) {   // the first res_p k-blocks of this CTA's rows of W_proj
         const int n_row = static_cast<int>(rank) * p.RP + row;
         const bool row_ok = row < p.RP && n_row < p.H;
-        load_rows(p.w_proj + static_cast<size_t>(row_ok ? n_row : 0) * p.Hp, row_ok, p.Hp, p.kbHp, p.res_col);
+        load_rows(p.w_proj + static_cast<size_t>(row_ok ? n_row : 0) * p.Hp, row_ok, p.Hp, p.res_p, p.res_col);
       }
       if (p.res_j) {   // the first res_j k-blocks of this CTA's first vocabulary tile (on the critical path of every step)
         const int v_row = static_cast<int>(rank) * p.RJ + row;

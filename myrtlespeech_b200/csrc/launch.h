@@ -203,7 +203,7 @@ struct ClusterDecodeArgs {
   const float* bias_p;
   int* sym;
   int* n_sym;
-  int res_p;               // != 0: this CTA's W_proj rows live in TMEM columns [res_col, res_col + 32 kbHp) for the whole decode
+  int res_p;               // leading k-blocks of this CTA's W_proj tile resident in TMEM columns [res_col, + 32 res_p)
   int res_col;
   int res_j, res_j_col;    // leading k-blocks of the first vocabulary tile resident in TMEM columns [res_j_col, + 32 res_j)
   const __nv_bfloat16* w_proj;    // [H][Hp] (only read when res_p)
