@@ -350,6 +350,7 @@ CDecPlan make_cdec_plan(int B, int V, int H, int Hp, int C, int NL = 1) {
 int g_decode_variant = 1;  // 1: one cluster per 16 utterances (default); 0: N-split over the grid with grid barriers
 int g_decode_cluster = 8;
 int g_decode_prof = 0;
+int g_decode_l_late = 0;
 int g_decode_res = 1;    // keep the projection weights resident in TMEM when they fit
 
 }  // namespace
@@ -368,6 +369,7 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "decode_cooperative")) set_decode_cooperative(value);
   if (!strcmp(key, "decode_prof")) g_decode_prof = value;
   if (!strcmp(key, "decode_resident")) g_decode_res = value;
+  if (!strcmp(key, "decode_l_late")) g_decode_l_late = value;
   if (!strcmp(key, "mega_kg")) g_kg_override = value;
   if (!strcmp(key, "decode_variant") && (value == 0 || value == 1)) g_decode_variant = value;
   if (!strcmp(key, "decode_cluster") && value >= 1 && value <= 16) g_decode_cluster = value;
@@ -748,7 +750,7 @@ static int decode_stack_impl(int cell, const void* f, const int32_t* lens, const
     a.o_amax = c.o_amax; a.o_part = c.o_part; a.o_state = c.o_state; a.o_bars = c.o_bars;
     a.f = static_cast<const __nv_bfloat16*>(f); a.lens = lens; a.bias_j = bias; a.table = gate_table; a.bias_up = bias_upper;
     a.bias_p = bias_proj;
-    a.sym = sym; a.n_sym = n_sym; a.prof = g_decode_prof;
+    a.sym = sym; a.n_sym = n_sym; a.prof = g_decode_prof; a.l_late = g_decode_l_late;
     {
       // Spare TMEM columns hold weights for the whole decode (32 columns per 64-wide k-block of a 128-row tile; A operand
       // of the TS-form MMA): first the projection tile, then leading k-blocks of the first vocabulary tile.  (Measured

@@ -568,9 +568,9 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
         for (int l = 1; l < NL; ++l)
           for (int m = 0; m < p.mtL; ++m) push(&tm_wu, ((l - 1) * C + static_cast<int>(rank)) * 4 * p.up + m * kBM, 2 * p.kbHp);
         for (int m = 0; m < p.mtP; ++m) push(&tm_wp, static_cast<int>(rank) * p.RP + m * kBM, p.kbHp, m == 0 ? p.res_p : 0);
-        push_l(0);
+        if (!p.l_late) push_l(0);
         for (int m = 0; m < p.mtJ; ++m) push(&tm_wj, static_cast<int>(rank) * p.RJ + m * kBM, p.kbH, m == 0 ? p.res_j : 0);
-        for (int m = 1; m < p.mtL; ++m) push_l(m);
+        for (int m = p.l_late ? 0 : 1; m < p.mtL; ++m) push_l(m);
       }
       if (prof) { g_dec_prof[10] = w_empty; g_dec_prof[11] = w_step; }
     }
@@ -657,13 +657,13 @@ greedy_decode_cluster_kernel(const __grid_constant__ CUtensorMap tm_wj, const __
       tc_fence_after();
       for (int m = 0; m < p.mtP; ++m)
         tile(smem_u32(hbuf(NL - 1, nxt)), p.kbHp, slotP0 + m, 0, 0, m == 0 ? p.res_p : 0, p.res_col);
-      tile(smem_u32(hbuf(0, nxt)), p.kbHp, 0);
+      if (!p.l_late) tile(smem_u32(hbuf(0, nxt)), p.kbHp, 0);
       t0 = prof ? clock64() : 0;
       mbar_wait(hjfull_bar, s & 1);
       if (prof) w_dep += clock64() - t0;
       tc_fence_after();
       for (int m = 0; m < p.mtJ; ++m) tile(smem_u32(hj), p.kbH, slotJ0 + m, 0, 0, m == 0 ? p.res_j : 0, p.res_j_col);
-      for (int m = 1; m < p.mtL; ++m) tile(smem_u32(hbuf(0, nxt)), p.kbHp, m);
+      for (int m = p.l_late ? 0 : 1; m < p.mtL; ++m) tile(smem_u32(hbuf(0, nxt)), p.kbHp, m);
     }
     if (prof) { g_dec_prof[12] = w_full; g_dec_prof[13] = w_dep; }
     if (elect_one()) umma_commit(fin_bar);

@@ -208,6 +208,7 @@ struct ClusterDecodeArgs {
   int res_j, res_j_col;    // leading k-blocks of the first vocabulary tile resident in TMEM columns [res_j_col, + 32 res_j)
   const __nv_bfloat16* w_proj;    // [H][Hp] (only read when res_p)
   const __nv_bfloat16* w_joint;   // [V][H]  (only read when res_j)
+  int l_late;              // experiment: issue all of W_hh . h(s+1) after the vocabulary product instead of tile 0 before it
   int prof;                // != 0: cluster 0 / rank 0 sums clock64 cycles per epilogue stage into g_dec_prof
 };
 int read_decode_prof(unsigned long long* out, int n);

@@ -22,6 +22,9 @@ f = torch.randn(B, T, H, device="cuda").bfloat16()
 lens = torch.full((B,), T, dtype=torch.int32)
 outs = {}
 from myrtlespeech_b200 import _lib
+for _k in ("decode_l_late", "decode_resident", "decode_cluster"):
+    if _k.upper() in os.environ:
+        _lib.load().rnnt_debug_set(_k.encode(), int(os.environ[_k.upper()]))
 for fused in (("cluster", "gridsync", False) if LAYERS == 1 else ("cluster", False)):
     dec.USE_FUSED_LOOP = bool(fused)
     _lib.load().rnnt_debug_set(b"decode_variant", 1 if fused == "cluster" else 0)
