@@ -317,7 +317,7 @@ CDecPlan make_cdec_plan(int B, int V, int H, int Hp, int C, int NL = 1) {
   d.up = up64((Hp + C - 1) / C); d.RP = up64((H + C - 1) / C); d.RJ = up64((V + C - 1) / C);
   d.mtL = d.up / 32; d.mtP = (d.RP + 127) / 128; d.mtJ = (d.RJ + 127) / 128;
   const int n_tiles = NL * d.mtL + d.mtP + d.mtJ;
-  if (n_tiles > 10) return d;
+  if (n_tiles > 10 || d.mtL > 4) return d;   // kMaxTiles / kMaxLTiles in decode.cu
   d.kbH = (H + 63) / 64; d.kbHp = (Hp + 63) / 64;
   d.tmem_cols = 32;
   while (d.tmem_cols < 32 * n_tiles) d.tmem_cols *= 2;   // two partial accumulators x 16 utterances per tile
