@@ -8,7 +8,10 @@ from myrtlespeech_b200 import _lib
 from bench import WORKLOADS, synth
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 kgs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
-B, T, U, V, H, desc = WORKLOADS[name]
+if "," in name:   # ad-hoc shape "B,T,U,V,H"
+    B, T, U, V, H = (int(x) for x in name.split(","))
+else:
+    B, T, U, V, H, desc = WORKLOADS[name]
 dev = torch.device("cuda", 0)
 f, g, W, bias, y, fl, yl = synth(B, T, U, V, H, 1234, dev)
 fd, gd, yd = f.to(dev).requires_grad_(True), g.to(dev).requires_grad_(True), y.to(dev)
