@@ -98,7 +98,7 @@ class RNNTGreedyDecoder(torch.nn.Module):
         lens = lengths.to(dev, torch.int32)
         pred = model.prediction
         if self.USE_FUSED_LOOP and T > 0:
-            packed = _pack_lstm_prediction(pred, B, Wb.size(0), H)
+            packed = self._packed_prediction(pred, B, Wb.size(0), H)
             if packed is not None:
                 table, whh, wproj, bproj, wup, bup, cell = packed
                 sym, n_sym = greedy_decode_lstm(fb, lens.contiguous(), Wb, bias, table, whh, wproj, bproj, blank, S,
@@ -142,6 +142,18 @@ class RNNTGreedyDecoder(torch.nn.Module):
                 step()
         sym_h, n_h = sym.cpu(), n_sym.cpu().tolist()
         return [sym_h[b, : n_h[b]].tolist() for b in range(B)]
+
+    def _packed_prediction(self, pred, B: int, V: int, H: int):
+        """``_pack_lstm_prediction`` memoised on the identity and in-place version of every prediction-network
+        parameter: repeated decodes with unchanged weights (evaluation, serving) skip the table product, the bf16
+        conversions and their launches; an optimiser step or ``load_state_dict`` bumps the versions and repacks."""
+        params = list(pred.parameters()) if isinstance(pred, torch.nn.Module) else []
+        key = (B, V, H, tuple((id(q), q._version, q.device) for q in params))
+        cache = self.__dict__.get("_pack_cache")
+        if not params or cache is None or cache[0] != key:
+            cache = (key, _pack_lstm_prediction(pred, B, V, H))
+            self.__dict__["_pack_cache"] = cache
+        return cache[1]
 
     def extra_repr(self) -> str:
         return f"blank_index={self.blank_index}, max_symbols_per_step={self.max_symbols_per_step}"

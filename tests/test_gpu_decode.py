@@ -233,3 +233,25 @@ def test_fused_stacked_lstm_decode_matches_oracle(seed, B, T, V, H, Hp, E, S, la
     assert calls, "the one-launch decode was not taken"
     assert [g for g, c in zip(got, clear) if c] == [w for w, c in zip(want, clear) if c]
     assert any(len(s) > 0 for s in got)
+
+
+def test_packed_prediction_weights_are_cached_and_invalidated():
+    """The decoder repacks the prediction network only when a parameter changed in place (optimiser step, load)."""
+    joint, pred, f, lens = _lstm_case(3, 5, 23, 40, 64, 64, 32)
+    model = RNNT(torch.nn.Identity(), pred, joint).cuda()
+    dec = RNNTGreedyDecoder(39, model, max_symbols_per_step=2)
+    import myrtlespeech_b200.post_process.rnn_t_greedy_decoder as D
+    calls, orig = [], D._pack_lstm_prediction
+    D._pack_lstm_prediction = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        a = dec(f.cuda(), lens)
+        b = dec(f.cuda(), lens)
+        assert a == b and len(calls) == 1
+        with torch.no_grad():
+            pred.proj.bias.add_(5.0)          # in-place update, as an optimiser step does
+        c = dec(f.cuda(), lens)
+        assert len(calls) == 2
+        want, margins = _oracle_transcripts(joint, pred, f, lens, 39, 2)
+        assert [g for g, m in zip(c, margins) if m > MARGIN] == [w for w, m in zip(want, margins) if m > MARGIN]
+    finally:
+        D._pack_lstm_prediction = orig
