@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from myrtlespeech_b200.model import RNNTJoint
 from myrtlespeech_b200.model.rnn_t import RNNT, RNNTPredictionNet
 from myrtlespeech_b200.post_process import RNNTGreedyDecoder
-B, T, V, H, S = 128, 500, 1024, 1024, 4
+B, T, V, H, S = int(os.environ.get("DEC_B", 128)), 500, 1024, 1024, 4
 E, HP = int(os.environ.get("PRED_E", 256)), int(os.environ.get("PRED_H", 512))
 BLANK_BIAS = float(os.environ.get("BLANK_BIAS", 0.0))
 LAYERS = int(os.environ.get("PRED_LAYERS", 1))
