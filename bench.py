@@ -253,6 +253,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_times = []   # per-step durations of the last timed() run (median and min are reported too)
+
     def timed(fn, steps):
         """Per-step CUDA events on the launch stream; L2 flushed between steps outside the events."""
         evs = []
@@ -262,7 +264,9 @@ def main():
             e0.record(); fn(); e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs)
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        step_times[:] = per_step
+        return sum(per_step)
 
     for _ in range(args.warmup):
         hot_step()
@@ -272,6 +276,7 @@ def main():
     if rank == 0:
         sampler.start()
     ms_total = timed(hot_step, args.steps)
+    rank0_steps = list(step_times)
     launches = int(lib.rnnt_debug_get(b"launches"))
     barrier()
 
@@ -400,7 +405,9 @@ def main():
         out = {
             "metric": METRIC, "value": round(B * world * args.steps / (ms_total * 1e-3), 2), "unit": "utterances/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": round(ms_total / args.steps, 4),
+            "ms_per_step_median": round(statistics.median(rank0_steps), 4), "ms_per_step_min": round(min(rank0_steps), 4),
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": desc, "B_per_gpu": B, "global_batch": B * world, "T": T, "U": U, "V": V, "H": H,
                        "parallelism": f"utterance-sharded dp{world}, one all-reduce of [dW|db|loss|n]",
