@@ -4,8 +4,12 @@ from ..model.rnn_t import RNNT, RNNTJoint, RNNTPredictionNet, _LinearEncoder
 from ..protos import rnn_t_pb2
 
 
-def build(rnn_t_cfg, input_features: int, output_features: int) -> Tuple[RNNT, int]:
+def build(rnn_t_cfg, input_features: int, output_features: int, input_channels: int = 1) -> Tuple[RNNT, int]:
     """Returns an :py:class:`.RNNT` based on the config and its number of output features.
+
+    ``input_features`` / ``input_channels`` are the sizes of the feature and channel axes of the model input
+    ``(batch, channels, features, seq_len)``, derived from the pre-processing steps as in the reference
+    (``builders/speech_to_text.py:249-272``; cf. ``builders/deep_speech_2.py`` taking the same arguments).
 
     Example:
         >>> from google.protobuf import text_format
@@ -32,7 +36,7 @@ def build(rnn_t_cfg, input_features: int, output_features: int) -> Tuple[RNNT, i
         if getattr(rnn_t_cfg, name) < 1:
             raise ValueError(f"{name}={getattr(rnn_t_cfg, name)} must be >= 1")
     encoder = _LinearEncoder(input_features, rnn_t_cfg.encoder_hidden_size, rnn_t_cfg.encoder_num_layers, H,
-                             rnn_type)
+                             rnn_type, input_channels=input_channels)
     prediction = RNNTPredictionNet(output_features, rnn_t_cfg.pred_embedding_size, rnn_t_cfg.pred_hidden_size,
                                    rnn_t_cfg.pred_num_layers, H, rnn_type)
     joint = RNNTJoint(H, output_features)

@@ -92,7 +92,7 @@ int sm_count() {
 struct Plan {
   int B, Tmax, Umax, U1, V, H, Vp, D;
   int max_tiles, slab_tiles;
-  size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_wt, o_h, o_dz, o_hs, o_hring, o_dzring, o_flags;
+  size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_lnp64, o_wt, o_h, o_dz, o_hs, o_hring, o_dzring, o_flags;
   int mega_ok, n_vt, n_ht, n_out, KG, C, P, NS;
   size_t total;
 };
@@ -115,11 +115,12 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
   p.o_lse = take(sizeof(float) * static_cast<size_t>(p.max_tiles) * kTileRows);
   p.o_lpb = take(sizeof(float) * cells);
   p.o_lpl = take(sizeof(float) * cells);
-  p.o_alpha = take(sizeof(float) * cells);
-  p.o_beta = take(sizeof(float) * cells);
+  p.o_alpha = take(sizeof(double) * cells);
+  p.o_beta = take(sizeof(double) * cells);
   p.o_c1 = take(sizeof(float) * cells);
   p.o_c2 = take(sizeof(float) * cells);
   p.o_lnpb = take(sizeof(float) * B);
+  p.o_lnp64 = take(sizeof(double) * B);
   p.o_wt = take(2 * static_cast<size_t>(H) * p.Vp);
   p.o_h = take(2 * static_cast<size_t>(p.slab_tiles) * kTileRows * H);
   p.o_dz = take(2 * static_cast<size_t>(p.slab_tiles) * kTileRows * p.Vp);
@@ -163,7 +164,8 @@ int check_dims(int B, int Tmax, int Umax, int V, int H) {
   if (B < 1 || Tmax < 1 || Umax < 0) return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d Umax=%d out of range", B, Tmax, Umax);
   if (V < 1 || V > 2048) return fail(RNNT_ERR_UNSUPPORTED, "V=%d must be in [1, 2048]", V);
   if (H < 8 || H % 8 != 0) return fail(RNNT_ERR_UNSUPPORTED, "H=%d must be a positive multiple of 8", H);
-  if (Umax + 1 > 1024) return fail(RNNT_ERR_UNSUPPORTED, "Umax+1=%d must be <= 1024", Umax + 1);
+  if (Umax + 1 > lattice_max_columns())
+    return fail(RNNT_ERR_UNSUPPORTED, "Umax+1=%d must be <= %d", Umax + 1, lattice_max_columns());
   return RNNT_OK;
 }
 
@@ -483,10 +485,11 @@ int rnnt_fused_forward(const void* f, const void* g, const void* W, const float*
     KLAUNCH(K_FWD, s, launch_joint_fwd(L, d, tm_h, tm_w, a, t0, nt, nc, s));
   }
   KLAUNCH(K_LATTICE, s, launch_lattice_alpha_beta(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl),
-                                                  w.at<float>(p.o_alpha), w.at<float>(p.o_beta), loss,
-                                                  w.at<float>(p.o_lnpb), s));
-  KLAUNCH(K_COEFS, s, launch_lattice_coefs(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl), w.at<float>(p.o_alpha),
-                                           w.at<float>(p.o_beta), loss, w.at<float>(p.o_c1), w.at<float>(p.o_c2), s));
+                                                  w.at<double>(p.o_alpha), w.at<double>(p.o_beta), loss,
+                                                  w.at<float>(p.o_lnpb), w.at<double>(p.o_lnp64), s));
+  KLAUNCH(K_COEFS, s, launch_lattice_coefs(L, w.at<float>(p.o_lpb), w.at<float>(p.o_lpl), w.at<double>(p.o_alpha),
+                                           w.at<double>(p.o_beta), w.at<double>(p.o_lnp64), w.at<float>(p.o_c1),
+                                           w.at<float>(p.o_c2), s));
   CUDA_TRY(cudaGetLastError());
   return RNNT_OK;
 }
@@ -587,15 +590,16 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
 size_t rnnt_lattice_workspace_bytes(int B, int Tmax, int Umax) {
   if (B < 1 || Tmax < 1 || Umax < 0) return 0;
   const size_t cells = static_cast<size_t>(B) * (Tmax + Umax + 1) * (Umax + 1);
-  return 3 * 1024 + align_up(sizeof(int) * (B + 1), 1024) * 3 + 6 * align_up(sizeof(float) * cells, 1024) +
-         align_up(sizeof(float) * B, 1024);
+  return 3 * 1024 + align_up(sizeof(int) * (B + 1), 1024) * 3 + 4 * align_up(sizeof(float) * cells, 1024) +
+         2 * align_up(sizeof(double) * cells, 1024) + align_up(sizeof(float) * B, 1024) + align_up(sizeof(double) * B, 1024);
 }
 
 int rnnt_lattice_forward(const float* lp_blank, const float* lp_label, const int32_t* f_lens_host,
                          const int32_t* y_lens_host, int B, int Tmax, int Umax, float* loss, float* c_blank,
                          float* c_label, void* workspace, size_t workspace_bytes, void* stream) {
   if (B < 1 || Tmax < 1 || Umax < 0) return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d Umax=%d out of range", B, Tmax, Umax);
-  if (Umax + 1 > 1024) return fail(RNNT_ERR_UNSUPPORTED, "Umax+1=%d must be <= 1024", Umax + 1);
+  if (Umax + 1 > lattice_max_columns())
+    return fail(RNNT_ERR_UNSUPPORTED, "Umax+1=%d must be <= %d", Umax + 1, lattice_max_columns());
   if (!lp_blank || !lp_label || !loss || !c_blank || !c_label || !workspace)
     return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
   int rc = check_lens(f_lens_host, y_lens_host, B, Tmax, Umax);
@@ -613,18 +617,19 @@ int rnnt_lattice_forward(const float* lp_blank, const float* lp_label, const int
   int* d_yl = reinterpret_cast<int*>(take(sizeof(int) * B));
   float* lpb = reinterpret_cast<float*>(take(sizeof(float) * cells));
   float* lpl = reinterpret_cast<float*>(take(sizeof(float) * cells));
-  float* al = reinterpret_cast<float*>(take(sizeof(float) * cells));
-  float* be = reinterpret_cast<float*>(take(sizeof(float) * cells));
+  double* al = reinterpret_cast<double*>(take(sizeof(double) * cells));
+  double* be = reinterpret_cast<double*>(take(sizeof(double) * cells));
   float* c1 = reinterpret_cast<float*>(take(sizeof(float) * cells));
   float* c2 = reinterpret_cast<float*>(take(sizeof(float) * cells));
   float* lnpb = reinterpret_cast<float*>(take(sizeof(float) * B));
+  double* lnp64 = reinterpret_cast<double*>(take(sizeof(double) * B));
   CUDA_TRY(cudaMemcpyAsync(d_fl, f_lens_host, sizeof(int) * B, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(d_yl, y_lens_host, sizeof(int) * B, cudaMemcpyHostToDevice, s));
   Lattice L{};
   L.tile_prefix = nullptr; L.f_lens = d_fl; L.y_lens = d_yl; L.B = B; L.Tmax = Tmax; L.U1max = U1; L.D = D;
   KLAUNCH(K_MISC, s, launch_nat_to_diag(L, lp_blank, lp_label, lpb, lpl, s));
-  KLAUNCH(K_LATTICE, s, launch_lattice_alpha_beta(L, lpb, lpl, al, be, loss, lnpb, s));
-  KLAUNCH(K_COEFS, s, launch_lattice_coefs(L, lpb, lpl, al, be, loss, c1, c2, s));
+  KLAUNCH(K_LATTICE, s, launch_lattice_alpha_beta(L, lpb, lpl, al, be, loss, lnpb, lnp64, s));
+  KLAUNCH(K_COEFS, s, launch_lattice_coefs(L, lpb, lpl, al, be, lnp64, c1, c2, s));
   KLAUNCH(K_MISC, s, launch_diag_to_nat(L, c1, c2, c_blank, c_label, s));
   CUDA_TRY(cudaGetLastError());
   return RNNT_OK;

@@ -15,140 +15,190 @@ namespace rnnt {
 
 namespace {
 
-constexpr int kPrefetch = 8;
-
-__device__ __forceinline__ float logaddexp_f(float a, float b) {
-  const float m = fmaxf(a, b);
-  const float n = fminf(a, b);
-  return m + kLn2 * lg2f(1.0f + ex2f((n - m) * kLog2e));
+// Precision.  alpha / beta are sums of up to T + U log-probabilities: at T = 500, U = 100, V = 1024 they reach
+// -4000, where one fp32 ulp is 4.9e-4 -- and the occupancies exp(alpha + beta + lp - lnP) inherit that *absolute*
+// error as a *relative* one, accumulated over ~600 dependent steps (measured: 1.6e-3 .. 2e-3 relative error of df,
+// dg, dW at the BASELINE shapes against an fp64 evaluation, tests/test_gpu_fullsize.py).  The state is therefore
+// carried and stored in fp64; only the bounded correction ln(1 + e^-|a-b|) <= ln 2 is evaluated in fp32
+// (ex2.approx / lg2.approx, absolute error ~1e-7).  Per cell and step this costs three DADDs and two conversions
+// on top of the fp32 chain.
+__device__ __forceinline__ double logaddexp_d(double a, double b) {
+  const double m = fmax(a, b);
+  const float diff = static_cast<float>(fmin(a, b) - m);   // <= 0; -inf-like operands give 0 or a huge negative
+  return m + static_cast<double>(kLn2 * lg2f(1.0f + ex2f(diff * kLog2e)));
 }
 
-__global__ void __launch_bounds__(1024, 1)
+constexpr double kNegD = -1.0e30;
+
+// NC = lattice columns per thread (column u = threadIdx.x + k * blockDim.x): 1 up to 1024 columns, 2 / 4 beyond.
+// kMaxT = launch bound: the usual U + 1 <= 256 gets a 256-thread variant whose register budget holds the prefetch
+// registers without spills.
+template <int NC, int kMaxT>
+__global__ void __launch_bounds__(kMaxT, 1)
 lattice_alpha_beta_kernel(Lattice L, const float* __restrict__ lpb, const float* __restrict__ lpl,
-                          float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ loss,
-                          float* __restrict__ lnp_beta) {
-  extern __shared__ float sbuf[];  // 2 x (blockDim.x + 2)
+                          double* __restrict__ alpha, double* __restrict__ beta, float* __restrict__ loss,
+                          float* __restrict__ lnp_beta, double* __restrict__ lnp64) {
+  constexpr int kPrefetch = NC == 1 ? 8 : (NC == 2 ? 4 : 2);
+  extern __shared__ double sbuf[];  // 2 x (NC * blockDim.x + 2)
   const int b = blockIdx.x;
   const bool is_beta = blockIdx.y == 1;
   const int T = L.f_lens[b];
   const int U = L.y_lens[b];
-  const int u = threadIdx.x;
-  const int stride = blockDim.x + 2;
-  float* s0 = sbuf;
-  float* s1 = sbuf + stride;
+  const int ncols = NC * blockDim.x;
+  const int stride = ncols + 2;
+  double* s0 = sbuf;
+  double* s1 = sbuf + stride;
   const size_t base = static_cast<size_t>(b) * L.D * L.U1max;
   const float* pb = lpb + base;
   const float* pl = lpl + base;
   const int dlast = T - 1 + U;
-  const bool col_ok = u <= U;
 
-  for (int i = threadIdx.x; i < 2 * stride; i += blockDim.x) sbuf[i] = kNeg;
+  for (int i = threadIdx.x; i < 2 * stride; i += blockDim.x) sbuf[i] = kNegD;
   __syncthreads();
 
-  float cb[kPrefetch], cl[kPrefetch];
+  float cb[NC][kPrefetch], cl[NC][kPrefetch];
 
   if (!is_beta) {
-    float* out = alpha + base;
+    double* out = alpha + base;
     // s?[u+1] holds the label-arc contribution arriving at column u+1; s?[0] stays kNeg.
-    float a_cur = (u == 0) ? 0.0f : kNeg;
+    double a_cur[NC];
 #pragma unroll
-    for (int i = 0; i < kPrefetch; ++i) {
-      const int d = i, t = d - u;
-      const bool ok = col_ok && t >= 0 && t < T && d <= dlast;
-      cb[i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-      cl[i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-    }
-    for (int d0 = 0; d0 <= dlast; d0 += kPrefetch) {
-      float nb[kPrefetch], nl[kPrefetch];
+    for (int c = 0; c < NC; ++c) a_cur[c] = (c == 0 && threadIdx.x == 0) ? 0.0 : kNegD;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int u = threadIdx.x + c * blockDim.x;
 #pragma unroll
       for (int i = 0; i < kPrefetch; ++i) {
-        const int d = d0 + kPrefetch + i, t = d - u;
-        const bool ok = col_ok && t >= 0 && t < T && d <= dlast;
-        nb[i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-        nl[i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
+        const int d = i, t = d - u;
+        const bool ok = u <= U && t >= 0 && t < T && d <= dlast;
+        cb[c][i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
+        cl[c][i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
+      }
+    }
+    for (int d0 = 0; d0 <= dlast; d0 += kPrefetch) {
+      float nb[NC][kPrefetch], nl[NC][kPrefetch];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int u = threadIdx.x + c * blockDim.x;
+#pragma unroll
+        for (int i = 0; i < kPrefetch; ++i) {
+          const int d = d0 + kPrefetch + i, t = d - u;
+          const bool ok = u <= U && t >= 0 && t < T && d <= dlast;
+          nb[c][i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
+          nl[c][i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
+        }
       }
 #pragma unroll
       for (int i = 0; i < kPrefetch; ++i) {
         const int d = d0 + i;
         if (d <= dlast) {  // uniform across the CTA
-          const int t = d - u;
-          const bool valid = col_ok && t >= 0 && t < T;
-          float* sw = (d & 1) ? s1 : s0;
-          float ob = kNeg, ol = kNeg;
-          if (valid) {
-            out[static_cast<size_t>(d) * L.U1max + u] = a_cur;
-            if (t + 1 < T) ob = a_cur + cb[i];
-            if (u < U) ol = a_cur + cl[i];
-            if (t == T - 1 && u == U) loss[b] = -(a_cur + cb[i]);
+          double* sw = (d & 1) ? s1 : s0;
+          double ob[NC];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const int u = threadIdx.x + c * blockDim.x;
+            const int t = d - u;
+            const bool valid = u <= U && t >= 0 && t < T;
+            double ol = kNegD;
+            ob[c] = kNegD;
+            if (valid) {
+              out[static_cast<size_t>(d) * L.U1max + u] = a_cur[c];
+              if (t + 1 < T) ob[c] = a_cur[c] + static_cast<double>(cb[c][i]);
+              if (u < U) ol = a_cur[c] + static_cast<double>(cl[c][i]);
+              if (t == T - 1 && u == U) {
+                const double lnp = a_cur[c] + static_cast<double>(cb[c][i]);
+                loss[b] = static_cast<float>(-lnp);
+                lnp64[b] = lnp;
+              }
+            }
+            sw[u + 1] = ol;
           }
-          sw[u + 1] = ol;
           __syncthreads();
-          a_cur = logaddexp_f(ob, sw[u]);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) a_cur[c] = logaddexp_d(ob[c], sw[threadIdx.x + c * blockDim.x]);
         }
       }
 #pragma unroll
-      for (int i = 0; i < kPrefetch; ++i) { cb[i] = nb[i]; cl[i] = nl[i]; }
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int i = 0; i < kPrefetch; ++i) { cb[c][i] = nb[c][i]; cl[c][i] = nl[c][i]; }
     }
   } else {
-    float* out = beta + base;
+    double* out = beta + base;
     // s?[u] holds beta of the previous (d+1) diagonal at column u.
-    float b_prev = kNeg;
+    double b_prev[NC];
 #pragma unroll
-    for (int i = 0; i < kPrefetch; ++i) {
-      const int d = dlast - i, t = d - u;
-      const bool ok = col_ok && t >= 0 && t < T && d >= 0;
-      cb[i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-      cl[i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-    }
-    for (int d0 = dlast; d0 >= 0; d0 -= kPrefetch) {
-      float nb[kPrefetch], nl[kPrefetch];
+    for (int c = 0; c < NC; ++c) b_prev[c] = kNegD;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int u = threadIdx.x + c * blockDim.x;
 #pragma unroll
       for (int i = 0; i < kPrefetch; ++i) {
-        const int d = d0 - kPrefetch - i, t = d - u;
-        const bool ok = col_ok && t >= 0 && t < T && d >= 0;
-        nb[i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-        nl[i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
+        const int d = dlast - i, t = d - u;
+        const bool ok = u <= U && t >= 0 && t < T && d >= 0;
+        cb[c][i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
+        cl[c][i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
+      }
+    }
+    for (int d0 = dlast; d0 >= 0; d0 -= kPrefetch) {
+      float nb[NC][kPrefetch], nl[NC][kPrefetch];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int u = threadIdx.x + c * blockDim.x;
+#pragma unroll
+        for (int i = 0; i < kPrefetch; ++i) {
+          const int d = d0 - kPrefetch - i, t = d - u;
+          const bool ok = u <= U && t >= 0 && t < T && d >= 0;
+          nb[c][i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
+          nl[c][i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
+        }
       }
 #pragma unroll
       for (int i = 0; i < kPrefetch; ++i) {
         const int d = d0 - i;
         if (d >= 0) {  // uniform across the CTA
-          const int t = d - u;
-          const bool valid = col_ok && t >= 0 && t < T;
-          const float* sr = ((d + 1) & 1) ? s1 : s0;
-          float* sw = (d & 1) ? s1 : s0;
-          float bv = kNeg;
-          if (valid) {
-            if (t == T - 1 && u == U) {
-              bv = cb[i];
-            } else {
-              const float x = (t + 1 < T) ? b_prev + cb[i] : kNeg;
-              const float y = (u < U) ? sr[u + 1] + cl[i] : kNeg;
-              bv = logaddexp_f(x, y);
+          const double* sr = ((d + 1) & 1) ? s1 : s0;
+          double* sw = (d & 1) ? s1 : s0;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const int u = threadIdx.x + c * blockDim.x;
+            const int t = d - u;
+            const bool valid = u <= U && t >= 0 && t < T;
+            double bv = kNegD;
+            if (valid) {
+              if (t == T - 1 && u == U) {
+                bv = static_cast<double>(cb[c][i]);
+              } else {
+                const double x = (t + 1 < T) ? b_prev[c] + static_cast<double>(cb[c][i]) : kNegD;
+                const double y = (u < U) ? sr[u + 1] + static_cast<double>(cl[c][i]) : kNegD;
+                bv = logaddexp_d(x, y);
+              }
+              out[static_cast<size_t>(d) * L.U1max + u] = bv;
+              if (d == 0) lnp_beta[b] = static_cast<float>(bv);
             }
-            out[static_cast<size_t>(d) * L.U1max + u] = bv;
-            if (d == 0) lnp_beta[b] = bv;
+            b_prev[c] = bv;
+            sw[u] = bv;
           }
-          b_prev = bv;
-          sw[u] = bv;
           __syncthreads();
         }
       }
 #pragma unroll
-      for (int i = 0; i < kPrefetch; ++i) { cb[i] = nb[i]; cl[i] = nl[i]; }
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int i = 0; i < kPrefetch; ++i) { cb[c][i] = nb[c][i]; cl[c][i] = nl[c][i]; }
     }
   }
 }
 
 __global__ void lattice_coefs_kernel(Lattice L, const float* __restrict__ lpb, const float* __restrict__ lpl,
-                                     const float* __restrict__ alpha, const float* __restrict__ beta,
-                                     const float* __restrict__ loss, float* __restrict__ c1,
+                                     const double* __restrict__ alpha, const double* __restrict__ beta,
+                                     const double* __restrict__ lnp64, float* __restrict__ c1,
                                      float* __restrict__ c2) {
   const int b = blockIdx.y;
   const int T = L.f_lens[b];
   const int U = L.y_lens[b];
   const int cells = L.D * L.U1max;
-  const float lnp = -loss[b];
+  const double lnp = lnp64[b];
   const size_t base = static_cast<size_t>(b) * cells;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) {
     const int d = i / L.U1max;
@@ -156,14 +206,14 @@ __global__ void lattice_coefs_kernel(Lattice L, const float* __restrict__ lpb, c
     const int t = d - u;
     float v1 = 0.0f, v2 = 0.0f;
     if (u <= U && t >= 0 && t < T) {
-      const float a = alpha[base + i];
-      const float xb = lpb[base + i];
+      const double a = alpha[base + i] - lnp;   // the large magnitudes cancel in fp64; the exponent is O(1..100)
+      const double xb = static_cast<double>(lpb[base + i]);
       if (t + 1 < T) {
-        v1 = ex2f((a + xb + beta[base + i + L.U1max] - lnp) * kLog2e);
+        v1 = ex2f(static_cast<float>(a + xb + beta[base + i + L.U1max]) * kLog2e);
       } else if (u == U) {
-        v1 = ex2f((a + xb - lnp) * kLog2e);
+        v1 = ex2f(static_cast<float>(a + xb) * kLog2e);
       }
-      if (u < U) v2 = ex2f((a + lpl[base + i] + beta[base + i + L.U1max + 1] - lnp) * kLog2e);
+      if (u < U) v2 = ex2f(static_cast<float>(a + static_cast<double>(lpl[base + i]) + beta[base + i + L.U1max + 1]) * kLog2e);
     }
     c1[base + i] = v1;
     c2[base + i] = v2;
@@ -211,20 +261,34 @@ void launch_diag_to_nat(const Lattice& L, const float* a_diag, const float* b_di
   diag_to_nat_kernel<<<dim3(bx, L.B), 256, 0, s>>>(L, a_diag, b_diag, a_nat, b_nat);
 }
 
-void launch_lattice_alpha_beta(const Lattice& L, const float* lpb, const float* lpl, float* alpha, float* beta,
-                               float* loss, float* lnp_beta, cudaStream_t s) {
-  int threads = ((L.U1max + 31) / 32) * 32;
+int lattice_max_columns() { return 4096; }
+
+void launch_lattice_alpha_beta(const Lattice& L, const float* lpb, const float* lpl, double* alpha, double* beta,
+                               float* loss, float* lnp_beta, double* lnp64, cudaStream_t s) {
+  const int nc = L.U1max <= 1024 ? 1 : (L.U1max <= 2048 ? 2 : 4);
+  int threads = (((L.U1max + nc - 1) / nc + 31) / 32) * 32;
   if (threads < 32) threads = 32;
-  const size_t smem = 2 * (threads + 2) * sizeof(float);
-  lattice_alpha_beta_kernel<<<dim3(L.B, 2), threads, smem, s>>>(L, lpb, lpl, alpha, beta, loss, lnp_beta);
+  const size_t smem = 2 * (static_cast<size_t>(nc) * threads + 2) * sizeof(double);
+  const dim3 grid(L.B, 2);
+  if (nc == 1 && threads <= 256) {
+    lattice_alpha_beta_kernel<1, 256><<<grid, threads, smem, s>>>(L, lpb, lpl, alpha, beta, loss, lnp_beta, lnp64);
+  } else if (nc == 1) {
+    lattice_alpha_beta_kernel<1, 1024><<<grid, threads, smem, s>>>(L, lpb, lpl, alpha, beta, loss, lnp_beta, lnp64);
+  } else if (nc == 2) {
+    lattice_alpha_beta_kernel<2, 1024><<<grid, threads, smem, s>>>(L, lpb, lpl, alpha, beta, loss, lnp_beta, lnp64);
+  } else {
+    // 2 x 4098 doubles = 65.6 KB of dynamic shared memory: above the 48 KB default (idempotent, per device)
+    cudaFuncSetAttribute(lattice_alpha_beta_kernel<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    lattice_alpha_beta_kernel<4, 1024><<<grid, threads, smem, s>>>(L, lpb, lpl, alpha, beta, loss, lnp_beta, lnp64);
+  }
 }
 
-void launch_lattice_coefs(const Lattice& L, const float* lpb, const float* lpl, const float* alpha,
-                          const float* beta, const float* loss, float* c1, float* c2, cudaStream_t s) {
+void launch_lattice_coefs(const Lattice& L, const float* lpb, const float* lpl, const double* alpha,
+                          const double* beta, const double* lnp64, float* c1, float* c2, cudaStream_t s) {
   const int cells = L.D * L.U1max;
   int bx = (cells + 255) / 256;
   if (bx > 64) bx = 64;
-  lattice_coefs_kernel<<<dim3(bx, L.B), 256, 0, s>>>(L, lpb, lpl, alpha, beta, loss, c1, c2);
+  lattice_coefs_kernel<<<dim3(bx, L.B), 256, 0, s>>>(L, lpb, lpl, alpha, beta, lnp64, c1, c2);
 }
 
 }  // namespace rnnt

@@ -12,11 +12,13 @@ namespace rnnt {
 // ---- lattice.cu -------------------------------------------------------------------------------
 // alpha and beta wavefronts (one CTA per utterance and direction), writes alpha/beta (diagonal
 // layout), loss[b] = -ln P(y|x) and lnp_beta[b] = beta[0,0] (consistency check).
-void launch_lattice_alpha_beta(const Lattice& L, const float* lpb, const float* lpl, float* alpha, float* beta,
-                               float* loss, float* lnp_beta, cudaStream_t s);
+// alpha / beta are fp64 (see lattice.cu, "Precision"); lnp64[b] = ln P(y|x) in fp64 for the coefficient kernel.
+void launch_lattice_alpha_beta(const Lattice& L, const float* lpb, const float* lpl, double* alpha, double* beta,
+                               float* loss, float* lnp_beta, double* lnp64, cudaStream_t s);
+int lattice_max_columns();   // largest U + 1 the wavefront kernel covers
 // c1 (blank-arc occupancy) and c2 (label-arc occupancy) per cell, diagonal layout.
-void launch_lattice_coefs(const Lattice& L, const float* lpb, const float* lpl, const float* alpha,
-                          const float* beta, const float* loss, float* c1, float* c2, cudaStream_t s);
+void launch_lattice_coefs(const Lattice& L, const float* lpb, const float* lpl, const double* alpha,
+                          const double* beta, const double* lnp64, float* c1, float* c2, cudaStream_t s);
 
 void launch_nat_to_diag(const Lattice& L, const float* a_nat, const float* b_nat, float* a_diag, float* b_diag,
                         cudaStream_t s);

@@ -127,6 +127,10 @@ class RNNT(torch.nn.Module):
     ``forward(x)`` takes ``x = ((audio_feats, labels), (audio_lens, label_lens))`` -- the labels are
     packed into the model input because the reference's loop passes only ``x`` to the model
     (``run/train.py:62-63``) -- and returns ``((joint_out, out_lens), hidden)``.
+
+    ``audio_feats`` has the layout the reference's collate function produces, ``(batch, channels, features,
+    seq_len)`` with the sequence axis last (``data/batch.py:45-107``, the input contract of
+    ``model/deep_speech_2.py:143-172``); the encoder owns the transposition to its own layout.
     """
 
     def __init__(self, encoder: torch.nn.Module, prediction: RNNTPredictionNet, joint: RNNTJoint):
@@ -150,13 +154,21 @@ class RNNT(torch.nn.Module):
 
 
 class _LinearEncoder(torch.nn.Module):
-    """Minimal (features -> RNN -> joint width) encoder used by the builder; batch-first."""
+    """Minimal (features -> RNN -> joint width) encoder used by the builder.
+
+    Input: ``(x, lens)`` with ``x`` of size ``(batch, channels, features, seq_len)`` -- the reference's model input
+    layout (``data/batch.py:45-107``; ``model/deep_speech_1.py`` / ``deep_speech_2.py`` take the same).  Channels and
+    features are flattened to one axis of width ``input_channels * input_features`` and the sequence axis is moved
+    in front of it for the batch-first RNN.  Output: ``((batch, seq_len, joint_hidden_size), lens)``.
+    """
 
     def __init__(self, input_features: int, hidden_size: int, num_layers: int, joint_hidden_size: int,
-                 rnn_type: str = "lstm"):
+                 rnn_type: str = "lstm", input_channels: int = 1):
         super().__init__()
         rnn_cls = {"lstm": torch.nn.LSTM, "gru": torch.nn.GRU}[rnn_type]
-        self.rnn = rnn_cls(input_features, hidden_size, num_layers=num_layers, batch_first=True)
+        self.input_features = input_features
+        self.input_channels = input_channels
+        self.rnn = rnn_cls(input_channels * input_features, hidden_size, num_layers=num_layers, batch_first=True)
         self.proj = torch.nn.Linear(hidden_size, joint_hidden_size)
         self.use_cuda = torch.cuda.is_available()
         if self.use_cuda:
@@ -164,7 +176,11 @@ class _LinearEncoder(torch.nn.Module):
 
     def forward(self, x):
         feats, lens = x
+        if feats.dim() != 4 or feats.size(1) != self.input_channels or feats.size(2) != self.input_features:
+            raise ValueError(f"encoder input must have size (batch, {self.input_channels}, {self.input_features}, "
+                             f"seq_len), got {tuple(feats.shape)}")
         if self.use_cuda:
             feats = feats.cuda()
-        out, hid = self.rnn(feats)
+        b, c, n, t = feats.shape
+        out, hid = self.rnn(feats.reshape(b, c * n, t).transpose(1, 2))
         return (self.proj(out), lens), hid

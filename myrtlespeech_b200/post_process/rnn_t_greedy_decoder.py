@@ -4,6 +4,7 @@ from typing import List
 import torch
 
 from ..functional import greedy_decode_lstm, greedy_decode_lstm_supported, greedy_step
+from ..model.rnn_t import JointHandle
 
 
 class RNNTGreedyDecoder(torch.nn.Module):
@@ -34,14 +35,21 @@ class RNNTGreedyDecoder(torch.nn.Module):
         return self._model
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, lengths: torch.Tensor) -> List[List[int]]:
+    def forward(self, x, lengths: torch.Tensor) -> List[List[int]]:
         r"""Decodes using a greedy strategy.
 
         Args:
-            x: ``(batch, seq_len, hidden)`` encoder output ``f`` (already projected to the joint
-                width), or raw features if ``model.encoder`` should be applied -- decided by the
-                last dimension matching ``model.joint.hidden_size``.
-            lengths: 1D integer tensor of valid frames per sequence.
+            x: what the model produced or consumes, told apart by type and rank (never by comparing sizes):
+
+                * the :py:class:`JointHandle` a training / evaluation forward pass returned -- the reference's
+                  report callback calls ``decoder(*last_output)`` (``run/run.py:94``), and the handle carries the
+                  encoder output ``f``;
+                * a 3-D tensor ``(batch, seq_len, joint_hidden_size)``: encoder output ``f``, already projected to
+                  the joint width (see :py:meth:`decode_encoded`);
+                * a 4-D tensor ``(batch, channels, features, seq_len)``: model input in the reference's layout
+                  (``data/batch.py:45-107``); ``model.encode`` is applied first.
+
+            lengths: 1D integer tensor of valid frames per sequence (of the model input for 4-D ``x``).
 
         Returns:
             ``List[List[int]]`` of emitted symbol ids per sequence.
@@ -54,7 +62,12 @@ class RNNTGreedyDecoder(torch.nn.Module):
         supported_dtypes = [torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64]
         if lengths.dtype not in supported_dtypes:
             raise ValueError(f"lengths.dtype={lengths.dtype} must be in {supported_dtypes}")
-        x_batch, seq_len, _ = x.size()
+        if isinstance(x, JointHandle):
+            x = x.f
+        if x.dim() not in (3, 4):
+            raise ValueError(f"x must be (batch, seq_len, hidden) or (batch, channels, features, seq_len), got {tuple(x.shape)}")
+        x_batch = x.size(0)
+        seq_len = x.size(1) if x.dim() == 3 else x.size(3)
         l_batch = len(lengths)
         if x_batch != l_batch:
             raise ValueError(f"batch size of x ({x_batch}) and lengths {l_batch} must be equal")
@@ -65,11 +78,19 @@ class RNNTGreedyDecoder(torch.nn.Module):
         was_training = model.training
         model.eval()
         try:
-            if x.size(2) != model.joint.hidden_size:
+            if x.dim() == 4:
                 x, lengths = model.encode(x, lengths)
-            return self._decode(x, lengths)
+            return self.decode_encoded(x, lengths)
         finally:
             model.train(was_training)
+
+    @torch.no_grad()
+    def decode_encoded(self, f: torch.Tensor, lengths: torch.Tensor) -> List[List[int]]:
+        """Decodes encoder output ``f`` of size ``(batch, seq_len, joint_hidden_size)`` directly."""
+        H = self._model.joint.hidden_size
+        if f.dim() != 3 or f.size(2) != H:
+            raise ValueError(f"encoder output must have size (batch, seq_len, {H}), got {tuple(f.shape)}")
+        return self._decode(f, lengths)
 
     #: run the whole loop (LSTM cell + projection + joint argmax + bookkeeping) as ONE launch when the prediction network
     #: is an LSTM or GRU of up to three layers (``rnnt_greedy_decode_lstm_stack`` / ``_gru_stack``); otherwise one CUDA
@@ -144,16 +165,29 @@ class RNNTGreedyDecoder(torch.nn.Module):
         return [sym_h[b, : n_h[b]].tolist() for b in range(B)]
 
     def _packed_prediction(self, pred, B: int, V: int, H: int):
-        """``_pack_lstm_prediction`` memoised on the identity and in-place version of every prediction-network
-        parameter: repeated decodes with unchanged weights (evaluation, serving) skip the table product, the bf16
-        conversions and their launches; an optimiser step or ``load_state_dict`` bumps the versions and repacks."""
+        """``_pack_lstm_prediction`` memoised over repeated decodes with unchanged weights (evaluation, serving): they
+        skip the table product, the bf16 conversions and their launches.
+
+        The cache is keyed by the identity, storage address and in-place version of every prediction-network
+        parameter, and validated by content: an fp64 (sum, sum of magnitudes) per parameter, computed on the device
+        and compared on every call (about twenty small reductions and one comparison against a 23 ms decode).  Updates
+        that bypass the version counter -- ``p.data.copy_``, ``p.data = ...``, an optimiser or EMA swap writing
+        ``.data`` -- therefore repack as well.  :py:meth:`invalidate_cache` drops the cache explicitly."""
         params = list(pred.parameters()) if isinstance(pred, torch.nn.Module) else []
-        key = (B, V, H, tuple((id(q), q._version, q.device) for q in params))
+        if not params:
+            return _pack_lstm_prediction(pred, B, V, H)
+        key = (B, V, H, tuple((id(q), q.data_ptr(), q._version, q.device, tuple(q.shape)) for q in params))
+        sums = [q.detach().double().sum() for q in params] + [q.detach().double().abs().sum() for q in params]
+        check = torch.stack([t.to(params[0].device) for t in sums])
         cache = self.__dict__.get("_pack_cache")
-        if not params or cache is None or cache[0] != key:
-            cache = (key, _pack_lstm_prediction(pred, B, V, H))
+        if cache is None or cache[0] != key or not torch.equal(cache[1], check):
+            cache = (key, check, _pack_lstm_prediction(pred, B, V, H))
             self.__dict__["_pack_cache"] = cache
-        return cache[1]
+        return cache[2]
+
+    def invalidate_cache(self) -> None:
+        """Forgets the packed prediction-network weights; the next decode repacks them."""
+        self.__dict__.pop("_pack_cache", None)
 
     def extra_repr(self) -> str:
         return f"blank_index={self.blank_index}, max_symbols_per_step={self.max_symbols_per_step}"
@@ -269,11 +303,3 @@ def _try_capture(step, state):
     for t, v in zip(tensors, saved):
         t.copy_(v)
     return graph
-
-
-def _select_hidden(mask: torch.Tensor, new, old):
-    if new is None or old is None:  # stateless prediction network, or first step (old state is "zeros")
-        return new
-    if isinstance(new, tuple):
-        return tuple(_select_hidden(mask, n, o) for n, o in zip(new, old))
-    return torch.where(mask[None, :, None], new, old)

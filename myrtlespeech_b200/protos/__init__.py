@@ -13,7 +13,14 @@ Messages (package ``myrtlespeech.protos``), each modelled on its CTC analog:
 * ``RNNTLoss``            <- ``protos/ctc_loss.proto:6-24``
 * ``RNNTGreedyDecoder``   <- ``protos/ctc_greedy_decoder.proto:5-8``
 * ``RNNT``                <- ``protos/deep_speech_2.proto`` / ``rnn.proto`` style model message
-* ``SpeechToText``        <- ``protos/speech_to_text.proto:13-35`` with the three new oneof members
+* ``Stage``, ``PreProcessStep`` (+ ``MFCC``, ``SpecAugment``, ``Standardize``, ``ContextFrames``)
+                          <- ``protos/stage.proto:6-10``, ``protos/pre_process_step.proto:9-63``, same field numbers
+* ``SpeechToText``        <- ``protos/speech_to_text.proto:13-35``: ``alphabet = 1`` and ``pre_process_step = 2`` as in
+                          the reference, plus the three new oneof members (8, 9, 10).  The reference's own members
+                          (``deep_speech_1/2``, ``ctc_*``: numbers 3-7) are not redeclared here -- they belong to
+                          models outside this path -- so a config that uses them is rejected by the parser, and a
+                          serialized RNN-T config is wire-compatible with the patched reference message
+                          (``speech_to_text_rnn_t.proto.patch``).
 
 The equivalent ``.proto`` text is kept next to this file (``*.proto``) for a
 maintainer who wants to drop it into the reference tree.
@@ -87,32 +94,74 @@ def _build():
     _field(m, "joint_hidden_size", 7, _F.TYPE_UINT32)
     _POOL.Add(fd)
 
-    # ---- speech_to_text.proto (RNN-T members only; CTC members stay in the reference) ---
-    fd = _file("speech_to_text", deps=("rnn_t", "rnn_t_loss", "rnn_t_greedy_decoder"))
+    # ---- stage.proto / pre_process_step.proto (schema identical to the reference's) ------
+    fd = _file("stage")
+    e = fd.enum_type.add()
+    e.name = "Stage"
+    for i, n in enumerate(("TRAIN", "EVAL", "TRAIN_AND_EVAL")):
+        v = e.value.add()
+        v.name, v.number = n, i
+    _POOL.Add(fd)
+
+    fd = _file("pre_process_step", deps=("stage",))
+    m = fd.message_type.add()
+    m.name = "PreProcessStep"
+    m.oneof_decl.add().name = "pre_process_step"
+    _field(m, "stage", 1, _F.TYPE_ENUM, f".{_PKG}.Stage")
+    _field(m, "mfcc", 2, _F.TYPE_MESSAGE, f".{_PKG}.MFCC", oneof_index=0)
+    _field(m, "standardize", 3, _F.TYPE_MESSAGE, f".{_PKG}.Standardize", oneof_index=0)
+    _field(m, "context_frames", 4, _F.TYPE_MESSAGE, f".{_PKG}.ContextFrames", oneof_index=0)
+    _field(m, "spec_augment", 5, _F.TYPE_MESSAGE, f".{_PKG}.SpecAugment", oneof_index=0)
+    m = fd.message_type.add()
+    m.name = "MFCC"
+    _field(m, "n_mfcc", 1, _F.TYPE_UINT32)
+    _field(m, "win_length", 2, _F.TYPE_UINT32)
+    _field(m, "hop_length", 3, _F.TYPE_UINT32)
+    _field(m, "legacy", 4, _F.TYPE_BOOL)
+    m = fd.message_type.add()
+    m.name = "SpecAugment"
+    for i, n in enumerate(("feature_mask", "time_mask", "n_feature_masks", "n_time_masks"), 1):
+        _field(m, n, i, _F.TYPE_UINT32)
+    fd.message_type.add().name = "Standardize"
+    m = fd.message_type.add()
+    m.name = "ContextFrames"
+    _field(m, "n_context", 1, _F.TYPE_UINT32)
+    _POOL.Add(fd)
+
+    # ---- speech_to_text.proto: the reference's message with the RNN-T oneof members added ----
+    fd = _file("speech_to_text", deps=("pre_process_step", "rnn_t", "rnn_t_loss", "rnn_t_greedy_decoder"))
     m = fd.message_type.add()
     m.name = "SpeechToText"
     for n in ("supported_models", "supported_losses", "supported_post_processes"):
         m.oneof_decl.add().name = n
     _field(m, "alphabet", 1, _F.TYPE_STRING)
-    # numbers 2-7 are taken in the reference (pre_process_step, deep_speech_1/2, ctc_loss, ctc decoders)
+    _field(m, "pre_process_step", 2, _F.TYPE_MESSAGE, f".{_PKG}.PreProcessStep", label=_F.LABEL_REPEATED)
+    # numbers 3-7 are the reference's deep_speech_1/2, ctc_loss and ctc decoders
     _field(m, "rnn_t", 8, _F.TYPE_MESSAGE, f".{_PKG}.RNNT", oneof_index=0)
     _field(m, "rnn_t_loss", 9, _F.TYPE_MESSAGE, f".{_PKG}.RNNTLoss", oneof_index=1)
     _field(m, "rnn_t_greedy_decoder", 10, _F.TYPE_MESSAGE, f".{_PKG}.RNNTGreedyDecoder", oneof_index=2)
+    # Extension for configs without an MFCC step (features computed outside the config, e.g. the synthetic batches of
+    # the tests): width of the feature axis.  Ignored when a pre_process_step fixes it.
     _field(m, "input_features", 11, _F.TYPE_UINT32)
     _POOL.Add(fd)
 
     def cls(name):
         return message_factory.GetMessageClass(_POOL.FindMessageTypeByName(f"{_PKG}.{name}"))
 
-    return cls("RNNTLoss"), cls("RNNTGreedyDecoder"), cls("RNNT"), cls("SpeechToText")
+    stage = _POOL.FindEnumTypeByName(f"{_PKG}.Stage")
+    return (cls("RNNTLoss"), cls("RNNTGreedyDecoder"), cls("RNNT"), cls("SpeechToText"), cls("PreProcessStep"),
+            SimpleNamespace(**{v.name: v.number for v in stage.values}, DESCRIPTOR=stage))
 
 
-RNNTLoss, RNNTGreedyDecoder, RNNT, SpeechToText = _build()
+RNNTLoss, RNNTGreedyDecoder, RNNT, SpeechToText, PreProcessStep, _Stage = _build()
 
 # ``from myrtlespeech_b200.protos import rnn_t_loss_pb2`` mirrors the reference's generated modules
 rnn_t_loss_pb2 = SimpleNamespace(RNNTLoss=RNNTLoss)
 rnn_t_greedy_decoder_pb2 = SimpleNamespace(RNNTGreedyDecoder=RNNTGreedyDecoder)
 rnn_t_pb2 = SimpleNamespace(RNNT=RNNT)
 speech_to_text_pb2 = SimpleNamespace(SpeechToText=SpeechToText)
+pre_process_step_pb2 = SimpleNamespace(PreProcessStep=PreProcessStep)
+stage_pb2 = SimpleNamespace(Stage=_Stage, TRAIN=_Stage.TRAIN, EVAL=_Stage.EVAL, TRAIN_AND_EVAL=_Stage.TRAIN_AND_EVAL)
 
-__all__ = ["rnn_t_loss_pb2", "rnn_t_greedy_decoder_pb2", "rnn_t_pb2", "speech_to_text_pb2"]
+__all__ = ["rnn_t_loss_pb2", "rnn_t_greedy_decoder_pb2", "rnn_t_pb2", "speech_to_text_pb2", "pre_process_step_pb2",
+           "stage_pb2"]

@@ -12,6 +12,8 @@ from typing import Dict, Optional, Union
 
 import torch
 
+from .callback import Callback, ModelCallback
+
 
 def _to_cuda(x):
     if isinstance(x, torch.Tensor):
@@ -24,11 +26,12 @@ def _to_cuda(x):
     return x
 
 
-class BF16MixedPrecision:
+class BF16MixedPrecision(Callback):
     """Drop-in for ``MixedPrecision`` in the callback list: ``on_batch_begin`` moves ``last_input`` to the GPU and
     opens a bf16 autocast region that ``on_loss_begin`` closes again (the loss runs in fp32)."""
 
     def __init__(self):
+        super().__init__()
         if not torch.cuda.is_available():
             raise ValueError("cuda not available")
         self.stack = contextlib.ExitStack()
@@ -44,31 +47,24 @@ class BF16MixedPrecision:
     def on_batch_end(self, **kwargs) -> None:
         self.stack.close()
 
-    def __getattr__(self, name):
-        if name.startswith("on_"):
-            return lambda **kwargs: None
-        raise AttributeError(name)
 
-
-class ClipGradNorm:
+class ClipGradNorm(ModelCallback):
     """``ClipGradNorm`` over the model's own parameters (there are no Apex master copies with bf16 autocast).
 
     Args:
-        model: the ``SeqToSeq``/``SpeechToText`` container or any module with ``parameters()``.
+        model: the ``SeqToSeq`` / ``SpeechToText`` container or any module with ``parameters()`` (the reference takes
+            the container too, ``run/callbacks/clip_grad_norm.py:23-32``).
         max_norm, norm_type: see :py:func:`torch.nn.utils.clip_grad_norm_`.
     """
 
     def __init__(self, model, max_norm: Union[float, int], norm_type: Union[float, int] = 2):
-        self.model = getattr(model, "model", model)
+        super().__init__(model)
         self.max_norm = max_norm
         self.norm_type = norm_type
         self.last_norm: Optional[float] = None
 
     def on_backward_end(self, **kwargs) -> None:
+        if not self.training:
+            return
         self.last_norm = float(torch.nn.utils.clip_grad_norm_(
             parameters=self.model.parameters(), max_norm=self.max_norm, norm_type=self.norm_type))
-
-    def __getattr__(self, name):
-        if name.startswith("on_"):
-            return lambda **kwargs: None
-        raise AttributeError(name)

@@ -5,14 +5,16 @@ The loop passes only ``x`` to the model (``run/train.py:62-63``: ``out, _ = seq_
 The reference's hook for rewriting the model input is ``Callback.on_batch_begin``: the handler stores ``x`` /
 ``y`` as ``last_input`` / ``last_target`` in its ``state_dict``, calls every callback with the state as keyword
 arguments, merges any returned dict back, and hands the possibly modified values to the loop
-(``run/callbacks/callback.py:221-254``).  The classes here follow that protocol by duck typing (same method names,
-``**kwargs`` in, ``Optional[dict]`` out), so they can be passed in ``fit(..., callbacks=[...])`` as they are or
-subclass the reference's ``Callback`` when it is importable.
+(``run/callbacks/callback.py:221-254``).  The classes here derive from the reference's ``Callback`` (see
+``callback.py`` in this package), so ``CallbackHandler.train(mode)`` (``run/callbacks/callback.py:483-491``,
+called by ``fit`` at ``run/train.py:51``) reaches them like any other callback.
 """
-from typing import Dict, List, Optional
+from typing import Callable, Dict, List, Optional
+
+from .callback import Callback
 
 
-class RNNTTraining:
+class RNNTTraining(Callback):
     """Packs the targets into the model input at the start of every batch.
 
     ``x = (feats, feat_lens)`` and ``y = (labels, label_lens)`` (the collate layout of
@@ -24,61 +26,65 @@ class RNNTTraining:
         (feats, feat_lens), (labels, label_lens) = kwargs["last_input"], kwargs["last_target"]
         return {"last_input": ((feats, labels), (feat_lens, label_lens))}
 
-    def __getattr__(self, name):
-        # every other hook of the reference's Callback protocol is a no-op
-        if name.startswith("on_"):
-            return lambda **kwargs: None
-        raise AttributeError(name)
 
-
-class ReportRNNTDecoder:
-    """Decodes every evaluation batch with an :py:class:`RNNTGreedyDecoder` and keeps transcripts and word errors,
-    the RNN-T counterpart of ``ReportCTCDecoder`` (``run/run.py:50-109``, decoder call at ``:94``).
+class ReportRNNTDecoder(Callback):
+    """Decodes every evaluation batch and reports the error rate: the RNN-T counterpart of ``ReportCTCDecoder``
+    (``run/run.py:50-109``), with the same report layout -- ``reports[<decoder class name>] = {"wer": float,
+    "transcripts": [(hypothesis, reference), ...]}``, ``wer`` in percent, ``-1.0`` until an evaluation epoch ends.
 
     Args:
-        decoder: ``decoder(feats, feat_lens) -> List[List[int]]``.
-        alphabet: maps ids to symbols with ``get_symbols`` (``data/alphabet.py:5``); ``None`` keeps ids.
+        rnnt_decoder: called as ``rnnt_decoder(*last_output)`` exactly like the reference calls its CTC decoder
+            (``run/run.py:94``); ``last_output`` is ``(JointHandle, frame_lens)`` and
+            :py:class:`RNNTGreedyDecoder` takes the encoder output out of the handle.
+        alphabet: converts sequences of indices to sequences of symbols (``data/alphabet.py:48``).
+        word_segmentor: groups symbols into words (``run/run.py:29-47``); :py:data:`None` scores symbols.
     """
 
-    def __init__(self, decoder, alphabet=None):
-        self.decoder = decoder
+    def __init__(self, rnnt_decoder, alphabet, word_segmentor: Optional[Callable] = None):
+        super().__init__()
+        self.rnnt_decoder = rnnt_decoder
         self.alphabet = alphabet
-        self.training = True
-        self.hypotheses: List = []
-        self.references: List = []
+        self.word_segmentor = word_segmentor
+        self.distances: List[int] = []
+        self.lengths: List[int] = []
 
-    def train(self, mode: bool = True):
-        self.training = mode
+    @property
+    def _name(self) -> str:
+        return self.rnnt_decoder.__class__.__name__
+
+    def _reset(self, **kwargs) -> None:
+        kwargs["reports"][self._name] = {"wer": -1.0, "transcripts": []}
+        self.distances = []
+        self.lengths = []
+
+    def on_train_begin(self, **kwargs) -> None:
+        self._reset(**kwargs)
 
     def on_epoch_begin(self, **kwargs) -> None:
-        self.hypotheses, self.references = [], []
+        self._reset(**kwargs)
+
+    def _process(self, sentence: List[int]) -> List[str]:
+        symbols = self.alphabet.get_symbols(sentence)
+        return symbols if self.word_segmentor is None else self.word_segmentor(symbols)
 
     def on_batch_end(self, **kwargs) -> None:
         if self.training:
             return
-        (feats, _labels), (feat_lens, _label_lens) = kwargs["last_input"]
-        labels, label_lens = kwargs["last_target"]
-        hyps = self.decoder(feats, feat_lens)
-        refs = [labels[b, : int(label_lens[b])].tolist() for b in range(len(hyps))]
-        if self.alphabet is not None:
-            hyps = [self.alphabet.get_symbols(h) for h in hyps]
-            refs = [self.alphabet.get_symbols(r) for r in refs]
-        self.hypotheses.extend(hyps)
-        self.references.extend(refs)
+        transcripts = kwargs["reports"][self._name]["transcripts"]
+        targets, target_lens = kwargs["last_target"][0], kwargs["last_target"][1]
+        acts = self.rnnt_decoder(*kwargs["last_output"])
+        for act, target, target_len in zip(acts, targets, target_lens):
+            act = self._process(act)
+            exp = self._process([int(e) for e in target[: int(target_len)]])
+            transcripts.append((act, exp))
+            self.distances.append(_levenshtein(act, exp))
+            self.lengths.append(len(exp))
 
-    def on_epoch_end(self, **kwargs) -> Optional[Dict]:
-        if self.training or not self.references:
-            return None
-        errs = sum(_levenshtein(h, r) for h, r in zip(self.hypotheses, self.references))
-        total = max(1, sum(len(r) for r in self.references))
-        reports = dict(kwargs.get("reports", {}))
-        reports[self.decoder.__class__.__name__ + "/error_rate"] = errs / total
-        return {"reports": reports}
-
-    def __getattr__(self, name):
-        if name.startswith("on_"):
-            return lambda **kwargs: None
-        raise AttributeError(name)
+    def on_epoch_end(self, **kwargs) -> None:
+        if self.training:
+            return
+        wer = float(sum(self.distances)) / max(1, sum(self.lengths)) * 100
+        kwargs["reports"][self._name]["wer"] = wer
 
 
 def _levenshtein(a, b) -> int:

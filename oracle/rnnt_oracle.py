@@ -272,6 +272,7 @@ def greedy_decode(
     max_symbols_per_step: int,
     faithful: bool = False,
     per_utterance_margin: bool = False,
+    tie_margin: Optional[float] = None,
 ) -> Tuple[List[List[int]], float]:
     """RNN-T greedy search for each utterance.
 
@@ -283,6 +284,10 @@ def greedy_decode(
     minima instead (utterances are independent, so a near-tie only excuses the
     utterance it occurs in).
 
+    With ``tie_margin`` a third value is returned: per utterance, the number of symbols emitted before the first
+    decode step whose top-2 margin is <= ``tie_margin`` (``len(hyp)`` if there is none).  A checker that runs in
+    different arithmetic can only be held to the transcript up to that point: every decision before it is clear.
+
     Ties resolve to the lowest index (numpy/torch argmax semantics).
     """
     f = np.asarray(f, dtype=np.float64)
@@ -292,8 +297,10 @@ def greedy_decode(
     out: List[List[int]] = []
     min_margin = np.inf
     margins: List[float] = []
+    clear_prefix: List[int] = []
     for b in range(f.shape[0]):
         hyp: List[int] = []
+        first_tie = -1
         min_margin = np.inf if per_utterance_margin else min_margin
         g, state = pred_step(None, None)
         for t in range(int(f_lens[b])):
@@ -308,12 +315,17 @@ def greedy_decode(
                 k = int(np.argmax(z))
                 top2 = np.partition(z, -2)[-2:]
                 min_margin = min(min_margin, float(top2[1] - top2[0]))
+                if tie_margin is not None and first_tie < 0 and float(top2[1] - top2[0]) <= tie_margin:
+                    first_tie = len(hyp)
                 if k == blank:
                     break
                 hyp.append(k)
                 g, state = pred_step(k, state)
         out.append(hyp)
         margins.append(float(min_margin))
+        clear_prefix.append(len(hyp) if first_tie < 0 else first_tie)
+    if tie_margin is not None:
+        return out, (margins if per_utterance_margin else float(min_margin)), clear_prefix
     if per_utterance_margin:
         return out, margins
     return out, float(min_margin)

@@ -89,6 +89,7 @@ def test_speech_to_text_builds():
     assert stt.loss.blank == 28 and stt.loss.reduction == "sum"
     assert stt.post_process.blank_index == 28 and stt.post_process.model is stt.model
     assert stt.pre_process_steps == []
+    assert (stt.model.encoder.input_features, stt.model.encoder.input_channels) == (8, 1)
 
 
 def test_speech_to_text_blank_mismatch_raises():
@@ -109,3 +110,58 @@ def test_speech_to_text_missing_member_raises(missing):
     cfg = text_format.Merge(text[:start] + text[end:], speech_to_text_pb2.SpeechToText())
     with pytest.raises(ValueError, match="not supported"):
         speech_to_text.build(cfg)
+
+
+STT_STEPS = '''
+alphabet: "abc_";
+pre_process_step { stage: TRAIN_AND_EVAL; mfcc { n_mfcc: 13; win_length: 400; hop_length: 160; } }
+pre_process_step { stage: TRAIN; spec_augment { feature_mask: 2; time_mask: 3; n_feature_masks: 1; n_time_masks: 1; } }
+pre_process_step { stage: TRAIN_AND_EVAL; standardize { } }
+pre_process_step { stage: TRAIN_AND_EVAL; context_frames { n_context: 2; } }
+input_features: 99;
+rnn_t { encoder_hidden_size: 8; encoder_num_layers: 1; pred_embedding_size: 8;
+        pred_hidden_size: 8; pred_num_layers: 1; joint_hidden_size: 16; }
+rnn_t_loss { blank_index: 3; reduction: SUM; }
+rnn_t_greedy_decoder { blank_index: 3; max_symbols_per_step: 4; }
+'''
+
+
+def test_input_sizes_are_derived_from_the_pre_process_steps():
+    """``builders/speech_to_text.py:249-272``: n_mfcc fixes the feature width (the ``input_features`` extension field is
+    then ignored), context frames the channel count; the encoder takes the collate layout (B, C, F, T)."""
+    stt = speech_to_text.build(text_format.Merge(STT_STEPS, speech_to_text_pb2.SpeechToText()))
+    enc = stt.model.encoder
+    assert (enc.input_features, enc.input_channels) == (13, 5)
+    assert [str(stage).split(".")[-1] for _, stage in stt.pre_process_steps] == ["TRAIN_AND_EVAL", "TRAIN", "TRAIN_AND_EVAL",
+                                                                                 "TRAIN_AND_EVAL"]
+    x = torch.randn(2, 5, 13, 7, device=next(enc.parameters()).device)
+    (out, lens), _ = enc((x, torch.tensor([7, 5])))
+    assert tuple(out.shape) == (2, 7, 16) and lens.tolist() == [7, 5]
+    with pytest.raises(ValueError, match="encoder input must have size"):
+        enc((torch.randn(2, 7, 13 * 5), torch.tensor([7, 5])))
+
+
+def test_proto_patch_applies_to_the_reference_schema(tmp_path):
+    """``protos/speech_to_text_rnn_t.proto.patch`` is an applicable unified diff against the reference's
+    ``speech_to_text.proto``, and the run-time descriptors agree with the patched text (names and field numbers)."""
+    import os
+    import re
+    import shutil
+    import subprocess
+    ref = "/root/reference/src/myrtlespeech/protos/speech_to_text.proto"
+    if not os.path.exists(ref) or shutil.which("patch") is None:
+        pytest.skip("needs the reference tree and patch(1)")
+    dst = tmp_path / "src" / "myrtlespeech" / "protos"
+    dst.mkdir(parents=True)
+    shutil.copy(ref, dst / "speech_to_text.proto")
+    patch = os.path.join(os.path.dirname(speech_to_text.__file__), "..", "protos", "speech_to_text_rnn_t.proto.patch")
+    r = subprocess.run(["patch", "-p1", "-i", os.path.abspath(patch)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    text = (dst / "speech_to_text.proto").read_text()
+    fields = speech_to_text_pb2.SpeechToText.DESCRIPTOR.fields_by_name
+    for name in ("alphabet", "pre_process_step", "rnn_t", "rnn_t_loss", "rnn_t_greedy_decoder", "input_features"):
+        m = re.search(r"\b%s = (\d+);" % name, text)
+        assert m and int(m.group(1)) == fields[name].number, name
+    for name, oneof in (("rnn_t", "supported_models"), ("rnn_t_loss", "supported_losses"),
+                        ("rnn_t_greedy_decoder", "supported_post_processes")):
+        assert fields[name].containing_oneof.name == oneof

@@ -203,6 +203,54 @@ def test_fused_lstm_decode_at_configs4_widths(decode_variant):
     assert all(len(g) <= int(l) * S for g, l in zip(got, lens))
 
 
+def test_fused_lstm_decode_at_configs4_full_length():
+    """BASELINE.json configs[4] at its full size (B=128, T=500, V=H=1024, max 4 symbols per frame; Hp=512, E=256): the
+    whole batch is decoded on the GPU in one launch and eight sampled utterances are replayed through the numpy oracle
+    (500 frames, up to 2000 dependent steps each).  The oracle runs in fp64 with the kernel's rounding points, the
+    kernel accumulates in fp32, so a decision whose top-2 logit margin is within accumulation noise may legitimately go
+    the other way, and every later step then sees a different label history.  The test therefore holds the GPU
+    transcript to the oracle's up to the first near-tie of each utterance (every decision before it is clear) and reports
+    how much of the transcripts that covers; utterances that agree to the end are counted separately."""
+    import json
+    import os
+    B, T, V, H, Hp, E, S = 128, 500, 1024, 1024, 512, 256, 4
+    joint, pred, f, _ = _lstm_case(13, B, T, V, H, Hp, E, lens=torch.full((B,), T, dtype=torch.int32), blank_bias=6.0)
+    lens = torch.full((B,), T, dtype=torch.int32)
+    lens[5] = 377   # one ragged row among the sampled ones
+    blank = V - 1
+    rows = [0, 5, 16, 37, 64, 90, 111, 127]
+    sub = torch.tensor(rows)
+    n = lambda t: None if t is None else t.detach().cpu().float().numpy()  # noqa: E731
+    r = pred.rnn
+    step = O.lstm_pred_step(n(pred.embedding.weight), [n(r.weight_ih_l0)], [n(r.weight_hh_l0)], [n(r.bias_ih_l0)],
+                            [n(r.bias_hh_l0)], n(pred.proj.weight), n(pred.proj.bias), faithful=True)
+    want, margins, clear = O.greedy_decode(f[sub].float().numpy(), lens[sub].numpy(), n(joint.fc.weight), n(joint.fc.bias),
+                                           step, blank, S, faithful=True, per_utterance_margin=True, tie_margin=MARGIN)
+    model = RNNT(torch.nn.Identity(), pred, joint).cuda()
+    got = RNNTGreedyDecoder(blank, model, max_symbols_per_step=S)(f.cuda(), lens)
+    identical, checked, total = 0, 0, 0
+    for i, row in enumerate(rows):
+        g, w, c = got[row], want[i], clear[i]
+        assert g[:c] == w[:c], (row, c, next(k for k in range(c) if g[k] != w[k]))
+        identical += int(g == w)
+        checked += len(w) if g == w else c
+        total += len(w)
+    report = dict(utterances=len(rows), identical=identical, symbols=total, symbols_checked=checked,
+                  excused_fraction=round(1.0 - checked / max(1, total), 4), tie_margin=MARGIN,
+                  symbols_emitted_gpu=sum(len(g) for g in got))
+    print("configs[4] T=500 decode parity:", report)
+    try:
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_decode_T500.json"), "w") as fh:
+            json.dump(report, fh)
+    except OSError:
+        pass
+    assert total > 8 * 100, "the sampled utterances emit too few symbols to be a meaningful check"
+    assert checked >= 0.5 * total, report
+    assert all(len(g) <= int(l) * S for g, l in zip(got, lens))
+
+
 STACK_CASES = [
     # seed, B, T, V, H, Hp, E, S, layers, cell
     (7, 5, 19, 40, 64, 64, 32, 2, 2, "lstm"),

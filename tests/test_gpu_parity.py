@@ -90,6 +90,7 @@ CASES = [
     (7, 1, 1, 0, 3, 8, 1, False),              # empty target, single frame
     (8, 3, 33, 0, 9, 16, 8, False),            # U = 0 for the whole batch
     (9, 2, 17, 15, 16, 8, 7, True),            # blank in the middle
+    (10, 2, 6, 1100, 12, 8, 11, True),         # more than 1024 lattice columns (two columns per lattice thread)
 ]
 
 
@@ -207,7 +208,8 @@ def test_known_answer_vector_through_lattice_entry():
 
 
 @pytest.mark.parametrize("shape", [(3, 7, 4, 6, 5), (4, 40, 17, 9, 8), (2, 33, 0, 4, 0), (2, 300, 120, 5, 4),
-                                   (3, 130, 127, 4, 3), (2, 90, 128, 4, 0), (5, 1, 9, 3, 1)])
+                                   (3, 130, 127, 4, 3), (2, 90, 128, 4, 0), (5, 1, 9, 3, 1),
+                                   (2, 24, 1500, 4, 1), (2, 12, 2600, 3, 2)])   # > 1024 columns: 2 / 4 columns per thread
 def test_lattice_entry_matches_oracle(shape):
     B, T, U, V, blank = shape
     rng = np.random.default_rng(B * 100 + T)

@@ -195,3 +195,23 @@ def test_decoder_length_overflow_raises_and_repr():
     assert "blank_index=3" in repr(dec) and "max_symbols_per_step=2" in repr(dec)
     with pytest.raises(ValueError):
         RNNTGreedyDecoder(0, _FakeModel(), max_symbols_per_step=0)
+
+
+def test_decoder_tells_inputs_apart_by_type_and_rank():
+    """JointHandle / (B, T, H) encoder output / (B, C, F, T) model input in the reference's collate layout
+    (data/batch.py:45-107); never by comparing a size with the joint width."""
+    dec = RNNTGreedyDecoder(3, _FakeModel())
+    # rank 3 whose last axis is not the joint width is an error, not "raw features"
+    with pytest.raises(ValueError, match=r"encoder output must have size \(batch, seq_len, 8\)"):
+        dec(torch.zeros(2, 3, 5), torch.tensor([3, 3]))
+    with pytest.raises(ValueError, match="x must be"):
+        dec(torch.zeros(2, 3), torch.tensor([3, 3]))
+    # rank 4: lengths are checked against the LAST axis, and the model's encoder is applied
+    with pytest.raises(ValueError, match="less than or equal to x seq_len"):
+        dec(torch.zeros(2, 1, 8, 3), torch.tensor([3, 4]))
+    with pytest.raises(AttributeError):      # _FakeModel has no encoder: proves the rank-4 branch calls model.encode
+        dec(torch.zeros(2, 1, 8, 3), torch.tensor([3, 3]))
+    # a JointHandle carries the encoder output; the length check runs against its time axis
+    h = JointHandle(torch.zeros(2, 3, 8), torch.zeros(2, 2, 8), torch.zeros(5, 8), None)
+    with pytest.raises(ValueError, match="less than or equal to x seq_len"):
+        dec(h, torch.tensor([3, 4]))
