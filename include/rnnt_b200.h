@@ -22,7 +22,8 @@
  *
  * Conventions: plain pointers and sizes only; every device buffer (inputs, outputs, workspace) is
  * allocated by the caller; calls are stream-ordered on `stream` (a cudaStream_t passed as void*), never
- * synchronise the host, keep no global mutable state and never allocate.  Return value 0 = success;
+ * synchronise the host, never allocate and keep no global mutable state (the rnnt_debug_* knobs at the end of
+ * this header are process-wide test / bring-up switches and the only exception).  Return value 0 = success;
  * otherwise one of RNNT_ERR_* and rnnt_last_error() describes it.  Length arrays are HOST int32 (they
  * originate on the host: src/myrtlespeech/data/batch.py:103-105); label ids are DEVICE int32
  * (src/myrtlespeech/builders/task_config.py:103-108).
@@ -33,7 +34,7 @@
  *   y   i32  [B][Umax]           label ids (never `blank`)
  *   loss f32 [B]                 -ln P(y_b | x_b)
  *   df  f32 [B][Tmax][H]   dg f32 [B][Umax+1][H]   dW f32 [V][H]   db f32 [V]
- * Constraints: H % 8 == 0, 1 <= V <= 2048, Umax + 1 <= 1024, 1 <= f_lens[b] <= Tmax, 0 <= y_lens[b] <= Umax.
+ * Constraints: H % 8 == 0, 1 <= V <= 2048, Umax + 1 <= 4096, 1 <= f_lens[b] <= Tmax, 0 <= y_lens[b] <= Umax.
  */
 #ifndef RNNT_B200_H_
 #define RNNT_B200_H_
@@ -59,6 +60,12 @@ const char* rnnt_last_error(void);
 
 /* Bytes of device workspace the fused calls need for these maxima.  Pure host arithmetic. */
 size_t rnnt_fused_workspace_bytes(int B, int Tmax, int Umax, int V, int H);
+
+/* Only the first rnnt_fused_state_bytes(...) bytes of the workspace carry information from rnnt_fused_forward to
+ * rnnt_fused_backward (lengths, row logsumexp, lp_blank / lp_label, arc occupancies: ~40 MB at B=32 T=500 U=100);
+ * the rest (~0.4 GB) is scratch.  A caller that keeps several forward passes alive may save just that prefix per
+ * pass and copy it to the front of any workspace of the right size before the matching backward call. */
+size_t rnnt_fused_state_bytes(int B, int Tmax, int Umax, int V, int H);
 
 /* Joint + log-softmax + alpha/beta.  Writes loss[B]; leaves lse / lp_blank / lp_label / arc
  * occupancies in `workspace` for rnnt_fused_backward.  The B*T*(U+1)*V logits are never written. */

@@ -20,6 +20,7 @@ SIGNATURES = {
     "rnnt_abi_version": (_c_int, []),
     "rnnt_last_error": (ctypes.c_char_p, []),
     "rnnt_fused_workspace_bytes": (_c_size_t, [_c_int] * 5),
+    "rnnt_fused_state_bytes": (_c_size_t, [_c_int] * 5),
     "rnnt_fused_forward": (_c_int, [_vp] * 7 + [_c_int] * 6 + [_vp, _vp, _c_size_t, _vp]),
     "rnnt_fused_backward": (_c_int, [_vp] * 7 + [_c_int] * 6 + [_vp] * 5 + [_vp, _c_size_t, _vp]),
     "rnnt_lattice_workspace_bytes": (_c_size_t, [_c_int] * 3),

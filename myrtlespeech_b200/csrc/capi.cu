@@ -77,14 +77,12 @@ cudaEvent_t pool_event() {
   } while (0)
 
 int sm_count() {
-  static int n = 0;
+  static int cache[kMaxDevices] = {};
+  const int dev = current_device();
+  int& n = cache[dev];
   if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      n = v;
-    else
-      n = 148;
+    int v = 0;
+    n = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
   }
   return n;
 }
@@ -94,7 +92,7 @@ struct Plan {
   int max_tiles, slab_tiles;
   size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_lnp64, o_wt, o_h, o_dz, o_hs, o_hring, o_dzring, o_flags;
   int mega_ok, n_vt, n_ht, n_out, KG, C, P, NS;
-  size_t total;
+  size_t state_bytes, total;
 };
 
 Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
@@ -115,10 +113,13 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
   p.o_lse = take(sizeof(float) * static_cast<size_t>(p.max_tiles) * kTileRows);
   p.o_lpb = take(sizeof(float) * cells);
   p.o_lpl = take(sizeof(float) * cells);
-  p.o_alpha = take(sizeof(double) * cells);
-  p.o_beta = take(sizeof(double) * cells);
   p.o_c1 = take(sizeof(float) * cells);
   p.o_c2 = take(sizeof(float) * cells);
+  // Everything up to here is the STATE the forward call leaves for the backward call (rnnt_fused_state_bytes); all
+  // that follows is scratch that either call may overwrite.
+  p.state_bytes = o;
+  p.o_alpha = take(sizeof(double) * cells);
+  p.o_beta = take(sizeof(double) * cells);
   p.o_lnpb = take(sizeof(float) * B);
   p.o_lnp64 = take(sizeof(double) * B);
   p.o_wt = take(2 * static_cast<size_t>(H) * p.Vp);
@@ -359,7 +360,7 @@ int g_decode_res = 1;    // keep the projection weights resident in TMEM when th
 
 extern "C" {
 
-int rnnt_abi_version(void) { return 1; }
+int rnnt_abi_version(void) { return 2; }
 
 const char* rnnt_last_error(void) { return g_err; }
 
@@ -425,6 +426,11 @@ int rnnt_debug_kernel_times(double* ms, long long* count, int n) {
 size_t rnnt_fused_workspace_bytes(int B, int Tmax, int Umax, int V, int H) {
   if (check_dims(B, Tmax, Umax, V, H) != RNNT_OK) return 0;
   return make_plan(B, Tmax, Umax, V, H).total;
+}
+
+size_t rnnt_fused_state_bytes(int B, int Tmax, int Umax, int V, int H) {
+  if (check_dims(B, Tmax, Umax, V, H) != RNNT_OK) return 0;
+  return make_plan(B, Tmax, Umax, V, H).state_bytes;
 }
 
 int rnnt_fused_forward(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,

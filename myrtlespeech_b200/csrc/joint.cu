@@ -816,10 +816,10 @@ greedy_step_kernel(const __nv_bfloat16* __restrict__ f, const float* __restrict_
 template <int EPI>
 void launch_slab_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmArgs& a,
                       int n_tiles, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (bool& c = configured[current_device()]; !c) {
     cudaFuncSetAttribute(slab_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total<EPI>());
-    configured = true;
+    c = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((n_tiles + 1) / 2 * 2);  // CTA pairs; an odd tail gets a ghost CTA
@@ -889,10 +889,10 @@ void launch_joint_dh(const Lattice& L, const JointDims& d, const CUtensorMap& tm
 
 void launch_joint_dw(const JointDims& d, const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, float* dW,
                      int n_tiles, int n_ctas, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (bool& c = configured[current_device()]; !c) {
     cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmem);
-    configured = true;
+    c = true;
   }
   DwArgs a{};
   a.dW = dW; a.V = d.V; a.H = d.H;

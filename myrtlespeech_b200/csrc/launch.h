@@ -9,6 +9,15 @@
 
 namespace rnnt {
 
+// Function attributes (dynamic shared memory opt-in) and occupancy answers are per DEVICE, the library is per
+// process: every cached flag / value is kept per device ordinal so that one process can drive several GPUs.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+
 // ---- lattice.cu -------------------------------------------------------------------------------
 // alpha and beta wavefronts (one CTA per utterance and direction), writes alpha/beta (diagonal
 // layout), loss[b] = -ln P(y|x) and lnp_beta[b] = beta[0,0] (consistency check).

@@ -12,6 +12,7 @@
 // Warp roles (320 threads): 0..3 = epilogue (TMEM lane quadrant = warp & 3), 4..7 = hgen, 8 = TMA producer,
 // 9 = TMEM allocator + MMA issuer (leader CTA only).
 #include <math.h>
+#include <stdlib.h>
 
 #include "launch.h"
 #include "ptx.cuh"
@@ -1200,7 +1201,8 @@ int smem_bytes_fwd_persist() { return kFwdSmem; }
 // Largest number of CTAs of the forward kernel that are co-resident for this cluster size (GPCs whose SM count is
 // not a multiple of the cluster size strand SMs: 148 CTAs fit as pairs, only 132 as 4-clusters on this B200).
 int max_ctas_fwd_persist(int csize) {
-  static int cached[5] = {0, 0, 0, 0, 0};
+  static int cache[kMaxDevices][5] = {};
+  int* cached = cache[current_device()];
   if (cached[csize]) return cached[csize];
   cudaFuncSetAttribute(fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
   cudaLaunchConfig_t cfg{};
@@ -1226,10 +1228,10 @@ int read_persist_prof(unsigned long long* out, int n) {
 
 void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
                         cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (bool& c = configured[current_device()]; !c) {
     cudaFuncSetAttribute(fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
-    configured = true;
+    c = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_ctas);
@@ -1249,7 +1251,8 @@ int smem_bytes_bwd_mega() { return kMegaSmem; }
 // Co-resident CTA capacity of the mega-kernel for a cluster size (its CTAs wait on one another: every CTA of the
 // grid must be resident at once).
 int max_ctas_bwd_mega(int csize) {
-  static int cached[5] = {0, 0, 0, 0, 0};
+  static int cache[kMaxDevices][5] = {};
+  int* cached = cache[current_device()];
   if (cached[csize]) return cached[csize];
   cudaFuncSetAttribute(bwd_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmem);
   cudaLaunchConfig_t cfg{};
@@ -1266,18 +1269,26 @@ int max_ctas_bwd_mega(int csize) {
   return cached[csize];
 }
 
+// A profiler that replays kernels (Nsight Compute) cannot replay a cooperative launch: the launch census of a run
+// under ncu stopped at this kernel.  ncu / nsys inject themselves through these variables; when one is present the
+// kernel is launched plainly (same grid, already sized to the co-resident capacity, see capi.cu).
+static bool profiler_attached() {
+  static const bool v = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ||
+                        getenv("NV_NSIGHT_INJECTION_PORT_BASE") || getenv("NVTX_INJECTION64_PATH");
+  return v;
+}
 static bool g_mega_cooperative = true;
-int bwd_mega_cooperative() { return g_mega_cooperative ? 1 : 0; }
+int bwd_mega_cooperative() { return (g_mega_cooperative && !profiler_attached()) ? 1 : 0; }
 void set_bwd_mega_cooperative(int v) { g_mega_cooperative = v != 0; }
 
 void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUtensorMap& tm_dz, const CUtensorMap& tm_wt,
                      const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, const CUtensorMap& tm_dz_st,
                      const BwdPArgs& a, int n_ctas, cudaStream_t s) {
-  static bool configured = false;
+  static bool configured[kMaxDevices] = {};
   bool& cooperative = g_mega_cooperative;   // the CTAs wait on one another: ask the driver to co-schedule the grid
-  if (!configured) {
+  if (bool& c = configured[current_device()]; !c) {
     cudaFuncSetAttribute(bwd_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmem);
-    configured = true;
+    c = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_ctas);
@@ -1290,13 +1301,15 @@ void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUt
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = cooperative ? 2 : 1;
+  cfg.numAttrs = (cooperative && !profiler_attached()) ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, bwd_mega_kernel, tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a);
-  if (e != cudaSuccess && cooperative) {
-    // cooperative + cluster launch not accepted by this driver: fall back to a plain launch (the grid is sized to
-    // the co-resident capacity reported by cudaOccupancyMaxActiveClusters, see capi.cu)
+  if (cooperative && (e == cudaErrorNotSupported || e == cudaErrorInvalidValue)) {
+    // cooperative + cluster launch not accepted by this driver / under this tool (a profiler replaying launches):
+    // this ONE launch falls back to a plain launch -- the grid is sized to the co-resident capacity reported by
+    // cudaOccupancyMaxActiveClusters (capi.cu), which is what the cooperative attribute would have enforced.  The
+    // process-wide preference is left alone (rnnt_debug_set("mega_cooperative", 0) switches it off explicitly);
+    // any other error is returned to the caller through cudaGetLastError().
     (void)cudaGetLastError();
-    cooperative = false;
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, bwd_mega_kernel, tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a);
   }

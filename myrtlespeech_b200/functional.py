@@ -1,5 +1,5 @@
 """Autograd-level entry points over the C-ABI library (no torch types cross the boundary)."""
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import torch
 
@@ -10,8 +10,14 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _on(t: torch.Tensor):
+    """Device guard: the library launches on the *current* device, so make the tensors' device current (a process
+    that drives several GPUs may call with tensors of any of them)."""
+    return torch.cuda.device(t.device)
 
 
 def _host_i32(x) -> torch.Tensor:
@@ -22,54 +28,131 @@ def _host_i32(x) -> torch.Tensor:
     return torch.tensor(list(x), dtype=torch.int32)
 
 
-class _FusedJointLoss(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, f, g, W, bias, y, f_lens, y_lens, blank):
-        lib = _lib.load()
-        if not f.is_cuda:
-            raise _lib.RNNTLibraryError("rnnt fused joint+loss needs CUDA tensors; there is no CPU fallback")
-        B, Tmax, H = f.shape
-        U1 = g.shape[1]
-        Umax = U1 - 1
-        V = W.shape[0]
-        fb = f.detach().to(torch.bfloat16).contiguous()
-        gb = g.detach().to(torch.bfloat16).contiguous()
-        Wb = W.detach().to(torch.bfloat16).contiguous()
-        bf = None if bias is None else bias.detach().to(torch.float32).contiguous()
-        yi = y.detach().to(device=f.device, dtype=torch.int32).contiguous()
-        if yi.dim() != 2 or yi.shape[0] != B or (Umax > 0 and yi.shape[1] != Umax):
-            raise ValueError(f"targets must have shape ({B}, {Umax}), got {tuple(yi.shape)}")
-        fl, yl = _host_i32(f_lens), _host_i32(y_lens)
-        if fl.numel() != B or yl.numel() != B:
-            raise ValueError(f"length tensors must have {B} entries")
-        nbytes = lib.rnnt_fused_workspace_bytes(B, Tmax, Umax, V, H)
-        if nbytes == 0:
-            raise ValueError(lib.rnnt_last_error().decode())
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=f.device)
+#: One scratch workspace per (device, stream).  A fused call needs ~0.4 GB of scratch at the target shape; only its first
+#: ``rnnt_fused_state_bytes`` bytes (~40 MB) carry information from the forward to the backward call.  The forward op
+#: returns that prefix as its own tensor (saved for backward by autograd) and the backward op copies it back to the
+#: front of the pooled workspace, so any number of live graphs share ONE scratch buffer per stream and nothing of
+#: 0.4 GB is allocated per step.  Calls on one stream are ordered, which is all the sharing needs.
+_ws_pool: dict = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_pool.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_pool[key] = ws
+    return ws
+
+
+def _align1k(x):
+    return (x + 1023) // 1024 * 1024
+
+
+def _state_bytes(B, Tmax, Umax, V, H):
+    """``rnnt_fused_state_bytes`` restated in Python so that the fake (meta) implementation works on symbolic sizes:
+    tile prefix + two length arrays + row lse + four per-cell fp32 arrays in the diagonal layout, each 1 KB aligned
+    (``csrc/capi.cu::make_plan``; ``tests/test_modules_cpu.py`` checks it against the library)."""
+    U1 = Umax + 1
+    max_tiles = B * ((Tmax + 15) // 16) * ((U1 + 7) // 8)
+    cells = B * (Tmax + U1) * U1
+    return (_align1k(4 * (B + 1)) + 2 * _align1k(4 * B) + _align1k(4 * max_tiles * 128) + 4 * _align1k(4 * cells))
+
+
+def _bf16c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+@torch.library.custom_op("rnnt_b200::fused_joint_loss", mutates_args=(), device_types="cuda")
+def _fused_joint_loss(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tensor,
+                      f_lens: torch.Tensor, y_lens: torch.Tensor, blank: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``(loss (B,) fp32, state (rnnt_fused_state_bytes,) uint8)``: joint + log-softmax + alpha/beta through
+    ``rnnt_fused_forward``; ``state`` is what ``rnnt_b200::fused_joint_loss_backward`` needs back."""
+    lib = _lib.load()
+    B, Tmax, H = f.shape
+    Umax = g.shape[1] - 1
+    V = W.shape[0]
+    fb, gb, Wb = _bf16c(f), _bf16c(g), _bf16c(W)
+    bf = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    yi = y.detach().to(device=f.device, dtype=torch.int32).contiguous()
+    fl, yl = _host_i32(f_lens), _host_i32(y_lens)
+    nbytes = lib.rnnt_fused_workspace_bytes(B, Tmax, Umax, V, H)
+    if nbytes == 0:
+        raise ValueError(lib.rnnt_last_error().decode())
+    sbytes = lib.rnnt_fused_state_bytes(B, Tmax, Umax, V, H)
+    with _on(fb):
+        ws = _workspace(nbytes, f.device)
+        ws[:sbytes].zero_()       # the per-cell arrays have cells no kernel writes (outside the lattice): keep them defined
         loss = torch.empty(B, dtype=torch.float32, device=f.device)
         _lib.check(lib.rnnt_fused_forward(_ptr(fb), _ptr(gb), _ptr(Wb), _ptr(bf), _ptr(yi), _ptr(fl), _ptr(yl),
-                                          B, Tmax, Umax, V, H, int(blank), _ptr(loss), _ptr(ws), nbytes, _stream()))
-        ctx.saved = (fb, gb, Wb, bf, yi, fl, yl, ws, nbytes)
-        ctx.dims = (B, Tmax, Umax, V, H, int(blank))
-        ctx.in_dtypes = (f.dtype, g.dtype, W.dtype, None if bias is None else bias.dtype)
-        return loss
+                                          B, Tmax, Umax, V, H, int(blank), _ptr(loss), _ptr(ws), nbytes,
+                                          _stream(f.device)))
+        state = ws[:sbytes].clone()
+    return loss, state
 
-    @staticmethod
-    def backward(ctx, grad_loss):
-        lib = _lib.load()
-        fb, gb, Wb, bf, yi, fl, yl, ws, nbytes = ctx.saved
-        B, Tmax, Umax, V, H, blank = ctx.dims
-        dev = fb.device
-        gl = grad_loss.detach().to(torch.float32).contiguous()
-        df = torch.empty(B, Tmax, H, dtype=torch.float32, device=dev)
-        dg = torch.empty(B, Umax + 1, H, dtype=torch.float32, device=dev)
-        dW = torch.empty(V, H, dtype=torch.float32, device=dev)
-        db = torch.empty(V, dtype=torch.float32, device=dev)
+
+@_fused_joint_loss.register_fake
+def _(f, g, W, bias, y, f_lens, y_lens, blank):
+    B, Tmax, H = f.shape
+    return (f.new_empty((B,), dtype=torch.float32),
+            f.new_empty((_state_bytes(B, Tmax, g.shape[1] - 1, W.shape[0], H),), dtype=torch.uint8))
+
+
+@torch.library.custom_op("rnnt_b200::fused_joint_loss_backward", mutates_args=(), device_types="cuda")
+def _fused_joint_loss_backward(grad_loss: torch.Tensor, f: torch.Tensor, g: torch.Tensor, W: torch.Tensor,
+                               bias: Optional[torch.Tensor], y: torch.Tensor, f_lens: torch.Tensor, y_lens: torch.Tensor,
+                               state: torch.Tensor, blank: int
+                               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``(df, dg, dW, db)`` in fp32 through ``rnnt_fused_backward``; ``state`` is the forward op's second output."""
+    lib = _lib.load()
+    B, Tmax, H = f.shape
+    Umax = g.shape[1] - 1
+    V = W.shape[0]
+    dev = f.device
+    fb, gb, Wb = _bf16c(f), _bf16c(g), _bf16c(W)
+    bf = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    yi = y.detach().to(device=dev, dtype=torch.int32).contiguous()
+    fl, yl = _host_i32(f_lens), _host_i32(y_lens)
+    gl = grad_loss.detach().to(torch.float32).contiguous()
+    nbytes = lib.rnnt_fused_workspace_bytes(B, Tmax, Umax, V, H)
+    df = torch.empty(B, Tmax, H, dtype=torch.float32, device=dev)
+    dg = torch.empty(B, Umax + 1, H, dtype=torch.float32, device=dev)
+    dW = torch.empty(V, H, dtype=torch.float32, device=dev)
+    db = torch.empty(V, dtype=torch.float32, device=dev)
+    with _on(fb):
+        ws = _workspace(nbytes, dev)
+        ws[: state.numel()].copy_(state)
         _lib.check(lib.rnnt_fused_backward(_ptr(fb), _ptr(gb), _ptr(Wb), _ptr(bf), _ptr(yi), _ptr(fl), _ptr(yl),
-                                           B, Tmax, Umax, V, H, blank, _ptr(gl), _ptr(df), _ptr(dg), _ptr(dW),
-                                           _ptr(db), _ptr(ws), nbytes, _stream()))
-        tf, tg, tW, tb = ctx.in_dtypes
-        return (df.to(tf), dg.to(tg), dW.to(tW), None if tb is None else db.to(tb), None, None, None, None)
+                                           B, Tmax, Umax, V, H, int(blank), _ptr(gl), _ptr(df), _ptr(dg), _ptr(dW),
+                                           _ptr(db), _ptr(ws), nbytes, _stream(dev)))
+    return df, dg, dW, db
+
+
+@_fused_joint_loss_backward.register_fake
+def _(grad_loss, f, g, W, bias, y, f_lens, y_lens, state, blank):
+    B, Tmax, H = f.shape
+    V = W.shape[0]
+    new = lambda *shape: f.new_empty(shape, dtype=torch.float32)  # noqa: E731
+    return new(B, Tmax, H), new(B, g.shape[1], H), new(V, H), new(V)
+
+
+def _setup_context(ctx, inputs, output):
+    f, g, W, bias, y, f_lens, y_lens, blank = inputs
+    _, state = output
+    ctx.save_for_backward(f, g, W, bias, y, f_lens, y_lens, state)
+    ctx.blank = blank
+    ctx.has_bias = bias is not None
+
+
+def _backward(ctx, grad_loss, _grad_state):
+    f, g, W, bias, y, f_lens, y_lens, state = ctx.saved_tensors
+    df, dg, dW, db = torch.ops.rnnt_b200.fused_joint_loss_backward(grad_loss, f, g, W, bias, y, f_lens, y_lens, state,
+                                                                    ctx.blank)
+    return (df.to(f.dtype), dg.to(g.dtype), dW.to(W.dtype), db.to(bias.dtype) if ctx.has_bias else None,
+            None, None, None, None)
+
+
+_fused_joint_loss.register_autograd(_backward, setup_context=_setup_context)
 
 
 def rnnt_joint_loss(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor],
@@ -77,9 +160,22 @@ def rnnt_joint_loss(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: Opt
     """Per-utterance ``-ln P(y|x)`` of the additive-tanh joint, fused with its lattice.
 
     f (B,T,H), g (B,U+1,H), W (V,H), bias (V) or None, y (B,U) int; returns (B,) fp32.
-    The (B,T,U+1,V) logits are never materialised.
+    The (B,T,U+1,V) logits are never materialised.  The arithmetic is the registered operator
+    ``torch.ops.rnnt_b200.fused_joint_loss`` (CUDA only; fake implementation and autograd formula registered, so it
+    traces under ``torch.compile`` / ``torch.export`` as one opaque node).
     """
-    return _FusedJointLoss.apply(f, g, W, bias, y, f_lens, y_lens, blank)
+    _lib.load()
+    if not f.is_cuda:
+        raise _lib.RNNTLibraryError("rnnt fused joint+loss needs CUDA tensors; there is no CPU fallback")
+    B = f.shape[0]
+    Umax = g.shape[1] - 1
+    if y.dim() != 2 or y.shape[0] != B or (Umax > 0 and y.shape[1] != Umax):
+        raise ValueError(f"targets must have shape ({B}, {Umax}), got {tuple(y.shape)}")
+    fl = f_lens if isinstance(f_lens, torch.Tensor) else torch.tensor(list(f_lens), dtype=torch.int32)
+    yl = y_lens if isinstance(y_lens, torch.Tensor) else torch.tensor(list(y_lens), dtype=torch.int32)
+    if fl.numel() != B or yl.numel() != B:
+        raise ValueError(f"length tensors must have {B} entries")
+    return torch.ops.rnnt_b200.fused_joint_loss(f, g, W, bias, y, fl, yl, int(blank))[0]
 
 
 class _LatticeLoss(torch.autograd.Function):
@@ -106,8 +202,9 @@ class _LatticeLoss(torch.autograd.Function):
         loss = torch.empty(B, dtype=torch.float32, device=logits.device)
         c1 = torch.empty(B, Tmax, U1, dtype=torch.float32, device=logits.device)
         c2 = torch.empty_like(c1)
-        _lib.check(lib.rnnt_lattice_forward(_ptr(lpb), _ptr(lpl), _ptr(fl), _ptr(yl), B, Tmax, Umax, _ptr(loss),
-                                            _ptr(c1), _ptr(c2), _ptr(ws), nbytes, _stream()))
+        with _on(logits):
+            _lib.check(lib.rnnt_lattice_forward(_ptr(lpb), _ptr(lpl), _ptr(fl), _ptr(yl), B, Tmax, Umax, _ptr(loss),
+                                                _ptr(c1), _ptr(c2), _ptr(ws), nbytes, _stream(logits.device)))
         ctx.save_for_backward(lp, c1, c2, yi)
         ctx.blank = blank
         ctx.in_dtype = logits.dtype
@@ -139,8 +236,9 @@ def greedy_joint_argmax(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias:
     V = W.shape[0]
     if out is None:
         out = torch.empty(B, dtype=torch.int32, device=f.device)
-    _lib.check(lib.rnnt_greedy_joint_argmax(_ptr(f), _ptr(g), _ptr(W), _ptr(bias), _ptr(t_idx), _ptr(out),
-                                            B, Tmax, V, H, _stream()))
+    with _on(f):
+        _lib.check(lib.rnnt_greedy_joint_argmax(_ptr(f), _ptr(g), _ptr(W), _ptr(bias), _ptr(t_idx), _ptr(out),
+                                                B, Tmax, V, H, _stream(f.device)))
     return out
 
 
@@ -152,9 +250,10 @@ def greedy_step(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: Optiona
     lib = _lib.load()
     B, Tmax, H = f.shape
     V = W.shape[0]
-    _lib.check(lib.rnnt_greedy_step(_ptr(f), _ptr(g), _ptr(W), _ptr(bias), _ptr(lens), _ptr(t_cur), _ptr(emitted),
-                                    _ptr(n_sym), _ptr(sym), sym.shape[1], _ptr(is_sym), _ptr(label), _ptr(active),
-                                    B, Tmax, V, H, int(blank), int(max_symbols), _stream()))
+    with _on(f):
+        _lib.check(lib.rnnt_greedy_step(_ptr(f), _ptr(g), _ptr(W), _ptr(bias), _ptr(lens), _ptr(t_cur), _ptr(emitted),
+                                        _ptr(n_sym), _ptr(sym), sym.shape[1], _ptr(is_sym), _ptr(label), _ptr(active),
+                                        B, Tmax, V, H, int(blank), int(max_symbols), _stream(f.device)))
 
 
 def greedy_decode_lstm_supported(B: int, V: int, H: int, Hp: int, n_layers: int = 1) -> bool:
@@ -195,8 +294,9 @@ def greedy_decode_lstm(f: torch.Tensor, lens: torch.Tensor, W: torch.Tensor, bia
     if cell not in ("lstm", "gru"):
         raise ValueError(f"cell={cell!r} must be 'lstm' or 'gru'")
     entry = lib.rnnt_greedy_decode_lstm_stack if cell == "lstm" else lib.rnnt_greedy_decode_gru_stack
-    _lib.check(entry(_ptr(f), _ptr(lens), _ptr(W), _ptr(bias), _ptr(gate_table), _ptr(W_hh),
-                     n_layers, _ptr(W_upper), _ptr(bias_upper), _ptr(W_proj), _ptr(bias_proj),
-                     B, Tmax, V, H, Hp, int(blank), int(max_symbols), _ptr(sym), cap,
-                     _ptr(n_sym), _ptr(ws), nbytes, _stream()))
+    with _on(f):
+        _lib.check(entry(_ptr(f), _ptr(lens), _ptr(W), _ptr(bias), _ptr(gate_table), _ptr(W_hh),
+                         n_layers, _ptr(W_upper), _ptr(bias_upper), _ptr(W_proj), _ptr(bias_proj),
+                         B, Tmax, V, H, Hp, int(blank), int(max_symbols), _ptr(sym), cap,
+                         _ptr(n_sym), _ptr(ws), nbytes, _stream(f.device)))
     return sym, n_sym

@@ -11,15 +11,21 @@ Tolerances (``north_star``: "loss and gradients within 1e-3 relative in fp32-acc
 * ``rel``    = ||got - ref||_F / ||ref||_F   < 1e-3 for every output;
 * ``relmax`` = max|got - ref| / max|ref|     < the per-output bound in ``RELMAX``.
 
-Why ``relmax`` of df / dg is allowed above 1e-3.  The kernels evaluate ``h = bf16(tanh.approx.f32(f + g))``; the
-checker evaluates ``bf16(tanh(f + g))`` with a correctly rounded tanh.  ``tanh.approx`` is accurate to ~2^-11, a
-quarter of a bf16 half-ulp, so roughly one ``h`` in eight rounds to the neighbouring bf16 value.  A flipped ``h``
-moves ``1 - h^2`` -- the factor every ``dpre = dh (1 - h^2)`` carries -- by ``2 h 2^-8``, i.e. ~1e-2 of that term;
-df (dg) sums U+1 (T) such terms with random signs, which leaves an element-wise error of a few 1e-3 of max|df|
-while the Frobenius error stays below 1e-3.  Against exact arithmetic the error of either side is dominated by
-the bf16 rounding of ``h`` itself (2^-9 on every element), so the flips do not make the result less accurate; they
-only make two bf16-faithful evaluations disagree.  dW, db and the loss average over ~1e6 rows and stay below 1e-3
-element-wise.
+Measured (round 2, both schedules): loss 1e-7, db 1e-6 .. 1e-5, dW 2e-5 (per-slab) / 2e-4 (persistent: one fp32 TMEM
+accumulator per dW block for the whole step), dg 2e-5 / relmax 8e-5, df 1.9e-4 / relmax 3.2e-3 .. 4.0e-3.
+
+Why ``relmax`` of df is allowed above 1e-3 -- the one bound that is not met element-wise.  The kernels evaluate
+``h = bf16(tanh.approx.f32(f + g))``; the checker evaluates ``bf16(tanh(f + g))`` with a correctly rounded tanh.
+``scripts/micro/tanh_flip.cu`` measures how often the two disagree on this input distribution: 3.4e-5 of all ``h``
+(1.2e-6 with an ``ex2`` + ``rcp`` tanh at half the MUFU rate, 7e-8 with libm ``tanhf``) -- always by exactly one bf16
+ulp.  At the target shape that is ~5e4 flipped values among 1.6e9.  A flipped ``h`` moves the factor ``1 - h^2`` of its
+``dpre = dh (1 - h^2)`` by ``2 |h| 2^-8 <= 7.8e-3``, i.e. by about 1.5 % of a typical term, and ``df[b,t,:]`` is a sum
+over only U+1 ~ 100 such terms dominated by the few lattice cells the alignment passes through, so the worst of the
+5e4 flips shows up as 3e-3 .. 4e-3 of max|df|; the 99.7 % of df elements without a flipped term agree to 1e-5.  dg
+(500 terms per element), dW and db (1.6e6 rows per element) average the flips away.  No implementation of tanh other
+than the checker's own removes the flips altogether (any last-bit difference flips some roundings), and against exact
+arithmetic the error of either side is dominated by the bf16 rounding of ``h`` itself (2^-9 on EVERY element), so the
+bound is a property of comparing two bf16-faithful evaluations, not a loss of accuracy.
 """
 import json
 import os
@@ -35,7 +41,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-3
 #: element-wise bounds, max|got - ref| / max|ref| (see the module docstring for df / dg)
-RELMAX = {"loss": 1e-4, "df": 6e-3, "dg": 6e-3, "dW": 1e-3, "db": 1e-3}
+RELMAX = {"loss": 1e-5, "df": 6e-3, "dg": 5e-4, "dW": 1e-3, "db": 1e-4}
 
 CONFIGS = {
     # name: (B, T, U, V, H)

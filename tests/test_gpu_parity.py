@@ -305,3 +305,55 @@ def test_subword_width_against_torchaudio():
     assert rel(got["loss"], loss.detach().cpu().numpy()) < 5e-3
     for name, t in (("df", ft), ("dg", gt), ("dW", Wt), ("db", bt)):
         assert rel(got[name], t.grad.cpu().numpy()) < 2e-2, name
+
+
+def test_custom_op_passes_opcheck():
+    """``torch.library.opcheck`` on the registered operator: schema (no undeclared mutation or aliasing), autograd
+    registration, fake-tensor implementation against the real one, and eager vs AOT-dispatched outputs and gradients with
+    dynamic shapes.  Gradients are accumulated with fp32 atomics whose order differs run to run, hence the tolerances."""
+    cfg = (23, 3, 14, 5, 29, 64, 28, True)
+    f, g, W, bias, y, fl, yl = make(*cfg)
+    args = (f.cuda().requires_grad_(True), g.cuda().requires_grad_(True), W.cuda().requires_grad_(True),
+            bias.cuda().requires_grad_(True), y.cuda(), torch.tensor(fl), torch.tensor(yl), 28)
+    res = torch.library.opcheck(torch.ops.rnnt_b200.fused_joint_loss, args, atol=1e-5, rtol=1e-3)
+    assert all(v == "SUCCESS" for v in res.values()), res
+    # no bias; bf16 leaves (the gradients come back in the leaves' dtype)
+    args = (f.bfloat16().cuda().requires_grad_(True), g.bfloat16().cuda().requires_grad_(True),
+            W.bfloat16().cuda().requires_grad_(True), None, y.cuda(), torch.tensor(fl), torch.tensor(yl), 28)
+    res = torch.library.opcheck(torch.ops.rnnt_b200.fused_joint_loss, args, atol=1e-2, rtol=2e-2)
+    assert all(v == "SUCCESS" for v in res.values()), res
+
+
+def test_fused_op_under_torch_compile_matches_eager():
+    """The operator is one opaque node for the compiler: a compiled function that wraps it gives the eager results."""
+    cfg = (24, 2, 12, 4, 17, 32, 16, True)
+    f, g, W, bias, y, fl, yl = make(*cfg)
+    fd, gd, Wd, bd, yd = f.cuda(), g.cuda(), W.cuda(), bias.cuda(), y.cuda()
+    flt, ylt = torch.tensor(fl), torch.tensor(yl)
+
+    def fn(f_, g_, W_, b_):
+        return M.rnnt_joint_loss(f_ * 1.0, g_, W_, b_, yd, flt, ylt, 16).sum()
+
+    want = fn(fd, gd, Wd, bd)
+    got = torch.compile(fn, backend="aot_eager")(fd, gd, Wd, bd)
+    assert rel(got.detach().cpu().numpy(), want.detach().cpu().numpy()) < 1e-6
+
+
+def test_two_live_graphs_share_one_scratch_workspace():
+    """Two forward passes are alive at once (gradient accumulation over two graphs): each keeps only its ~state prefix,
+    the scratch workspace is shared, and both backward passes give the right gradients."""
+    a = make(31, 2, 20, 6, 29, 64, 28, True)
+    b = make(32, 3, 15, 4, 29, 64, 28, True)
+    outs = []
+    leaves = []
+    for f, g, W, bias, y, fl, yl in (a, b):
+        fd = f.cuda().requires_grad_(True); gd = g.cuda().requires_grad_(True)
+        Wd = W.cuda().requires_grad_(True); bd = bias.cuda().requires_grad_(True)
+        outs.append(M.rnnt_joint_loss(fd, gd, Wd, bd, y.cuda(), torch.tensor(fl), torch.tensor(yl), 28).sum())
+        leaves.append((fd, gd, Wd, bd))
+    outs[0].backward()      # the second forward pass ran in between and overwrote the scratch
+    outs[1].backward()
+    for (f, g, W, bias, y, fl, yl), (fd, gd, Wd, bd) in zip((a, b), leaves):
+        ref = O.rnnt_joint_loss(f.numpy(), g.numpy(), W.numpy(), bias.numpy(), y.numpy(), fl, yl, 28, faithful=True)
+        for k, t in (("df", fd), ("dg", gd), ("dW", Wd), ("db", bd)):
+            assert rel(t.grad.cpu().numpy(), ref[k]) < TOL, k

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_workspace_arithmetic():
     lib = _lib.load()
-    assert lib.rnnt_abi_version() == 1
+    assert lib.rnnt_abi_version() == 2
     small = lib.rnnt_fused_workspace_bytes(4, 200, 50, 29, 512)
     big = lib.rnnt_fused_workspace_bytes(32, 500, 100, 1024, 1024)
     assert 0 < small < big < 1 << 30
@@ -215,3 +215,24 @@ def test_decoder_tells_inputs_apart_by_type_and_rank():
     h = JointHandle(torch.zeros(2, 3, 8), torch.zeros(2, 2, 8), torch.zeros(5, 8), None)
     with pytest.raises(ValueError, match="less than or equal to x seq_len"):
         dec(h, torch.tensor([3, 4]))
+
+
+def test_custom_op_is_registered_with_a_fake_implementation():
+    """``torch.ops.rnnt_b200.fused_joint_loss`` / ``..._backward`` exist, and their fake (meta) implementations infer the
+    output shapes without a GPU -- what ``torch.compile`` / ``torch.export`` need to trace through the ctypes call."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from myrtlespeech_b200 import functional as F
+    lib = _lib.load()
+    for dims in [(32, 500, 100, 1024, 1024), (3, 37, 11, 300, 128), (1, 1, 0, 3, 8), (2, 6, 1100, 12, 8), (4, 200, 50, 29, 512)]:
+        assert lib.rnnt_fused_state_bytes(*dims) == F._state_bytes(*dims), dims
+        assert 0 < lib.rnnt_fused_state_bytes(*dims) < lib.rnnt_fused_workspace_bytes(*dims)
+    with FakeTensorMode():
+        f = torch.empty(3, 37, 128, device="cuda"); g = torch.empty(3, 12, 128, device="cuda")
+        W = torch.empty(300, 128, device="cuda"); b = torch.empty(300, device="cuda")
+        y = torch.empty(3, 11, dtype=torch.int32, device="cuda")
+        fl = torch.empty(3, dtype=torch.int64); yl = torch.empty(3, dtype=torch.int64)
+        loss, state = torch.ops.rnnt_b200.fused_joint_loss(f, g, W, b, y, fl, yl, 299)
+        assert tuple(loss.shape) == (3,) and loss.dtype == torch.float32 and loss.device.type == "cuda"
+        assert state.dtype == torch.uint8 and state.numel() == F._state_bytes(3, 37, 11, 300, 128)
+        grads = torch.ops.rnnt_b200.fused_joint_loss_backward(loss, f, g, W, None, y, fl, yl, state, 299)
+        assert [tuple(t.shape) for t in grads] == [(3, 37, 128), (3, 12, 128), (300, 128), (300,)]
