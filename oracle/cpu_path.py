@@ -12,8 +12,9 @@ a library transducer loss, exactly as its CTC path is stock ``LogSoftmax`` + ``t
 in fp32 on the host cores.  It materialises the (B,T,U+1,V) tensor, as the reference
 convention would.
 """
+import os
 import time
-from typing import Dict
+from typing import Dict, Optional
 
 import torch
 
@@ -33,8 +34,14 @@ def step(f, g, W, bias, y, f_lens, y_lens, blank: int) -> Dict[str, torch.Tensor
     return dict(loss=loss.detach(), df=f.grad, dg=g.grad, dW=W.grad, db=bias.grad)
 
 
-def time_steps(B: int, T: int, U: int, V: int, H: int, steps: int, warmup: int, seed: int = 1234) -> Dict:
-    """Times `steps` fwd+bwd passes on synthetic inputs of the given shape; returns utt/s and metadata."""
+def time_steps(B: int, T: int, U: int, V: int, H: int, steps: int, warmup: int, seed: int = 1234,
+               threads: Optional[int] = None) -> Dict:
+    """Times `steps` fwd+bwd passes on synthetic inputs of the given shape; returns utt/s and metadata.
+
+    ``threads`` (default: every host core, ``os.cpu_count()``) is set explicitly with ``torch.set_num_threads`` so that
+    the figure does not depend on ``OMP_NUM_THREADS`` -- ``torchrun`` sets it to 1 for its workers."""
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
     gen = torch.Generator().manual_seed(seed)
     f = torch.randn(B, T, H, generator=gen)
     g = torch.randn(B, U + 1, H, generator=gen)
