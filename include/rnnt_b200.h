@@ -34,7 +34,7 @@
  *   y   i32  [B][Umax]           label ids (never `blank`)
  *   loss f32 [B]                 -ln P(y_b | x_b)
  *   df  f32 [B][Tmax][H]   dg f32 [B][Umax+1][H]   dW f32 [V][H]   db f32 [V]
- * Constraints: H % 8 == 0, 1 <= V <= 2048, Umax + 1 <= 4096, 1 <= f_lens[b] <= Tmax, 0 <= y_lens[b] <= Umax.
+ * Constraints: H % 8 == 0, 1 <= V <= 8192, Umax + 1 <= 4096, 1 <= f_lens[b] <= Tmax, 0 <= y_lens[b] <= Umax.
  */
 #ifndef RNNT_B200_H_
 #define RNNT_B200_H_

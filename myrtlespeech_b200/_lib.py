@@ -9,7 +9,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librnnt_b200.so")
+LIB_PATH = os.environ.get("RNNT_LIB_PATH") or os.path.join(_HERE, "lib", "librnnt_b200.so")   # override: bring-up builds
 
 _c_int = ctypes.c_int
 _c_size_t = ctypes.c_size_t

@@ -27,14 +27,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
     prof = ["-DRNNT_PROFILE"] if os.environ.get("RNNT_PROFILE") == "1" else []
-    cmd = [nvcc] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + ["-lcudart"]
+    prof += os.environ.get("RNNT_EXTRA_NVCC_FLAGS", "").split()     # bring-up experiments, e.g. -DRNNT_EXP_STAGES=6
+    out = os.environ.get("RNNT_LIB_OUT", OUT)
+    cmd = [nvcc] + NVCC_FLAGS + prof + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES + ["-lcudart"]
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building librnnt_b200.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

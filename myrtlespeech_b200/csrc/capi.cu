@@ -150,7 +150,7 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
   p.C = p.n_out * p.KG;
   p.P = kMaxPersistCtas / 2 - p.C;
   p.NS = g_ring_slots;
-  p.mega_ok = p.C <= 40 && p.P >= 1;
+  p.mega_ok = p.C <= 40 && p.P >= 1 && p.Vp <= 2048;   // 8 V chunks / 2048 bias columns in the mega-kernel
   p.o_hring = p.o_dzring = p.o_flags = 0;
   if (p.mega_ok) {
     p.o_hring = take(2 * static_cast<size_t>(p.P) * kMaxRingSlots * 2 * kTileRows * H);
@@ -163,7 +163,7 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
 
 int check_dims(int B, int Tmax, int Umax, int V, int H) {
   if (B < 1 || Tmax < 1 || Umax < 0) return fail(RNNT_ERR_INVALID_ARGUMENT, "B=%d Tmax=%d Umax=%d out of range", B, Tmax, Umax);
-  if (V < 1 || V > 2048) return fail(RNNT_ERR_UNSUPPORTED, "V=%d must be in [1, 2048]", V);
+  if (V < 1 || V > 8192) return fail(RNNT_ERR_UNSUPPORTED, "V=%d must be in [1, 8192]", V);
   if (H < 8 || H % 8 != 0) return fail(RNNT_ERR_UNSUPPORTED, "H=%d must be a positive multiple of 8", H);
   if (Umax + 1 > lattice_max_columns())
     return fail(RNNT_ERR_UNSUPPORTED, "Umax+1=%d must be <= %d", Umax + 1, lattice_max_columns());

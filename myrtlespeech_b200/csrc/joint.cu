@@ -33,7 +33,7 @@ constexpr int kStageBytes = kAStage + kBStage;
 constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
-constexpr int kMaxBiasCols = 2048;          // V (rounded up to chunks) supported by the smem bias table
+constexpr int kMaxBiasCols = 8192;          // V (rounded up to chunks) supported by the smem bias table (32 KB)
 constexpr int kDhPitch = 68;                // fp32 pitch of the dpre tile (16-byte aligned rows, conflict-free 128-bit access)
 
 enum Epi { kFwd = 0, kDz = 1, kDh = 2 };

@@ -31,7 +31,8 @@ constexpr int kPThreads = 320;
 constexpr int kEpiThreads = 128;
 constexpr int kHgenThreads = 128;
 constexpr int kTmemCols = 512;
-constexpr int kMaxBiasCols = 2048;
+constexpr int kMaxBiasCols = 8192;      // forward kernel: bias table of up to 8192 vocabulary columns (32 KB)
+constexpr int kMegaBiasCols = 2048;     // backward mega-kernel (shapes beyond it take the per-slab kernels)
 // Warp roles.  The scheduler of an SM sub-partition (warp id % 4) favours the highest warp id among its eligible
 // warps, so the latency-critical single-issuer warps (TMA producer, MMA issuer) get the highest ids of their
 // sub-partitions; epilogue warps must satisfy (warp id % 4) == TMEM lane quadrant.
@@ -502,7 +503,7 @@ constexpr int kUnionBytes = 2 * kBM * kDhPitch * 4;  // dh fp32 tiles (69,632 B)
 constexpr int kCStageBytes = 3 * 16384;
 constexpr int kMaxNS = 4;
 constexpr int kMaxVChunks = 8;
-constexpr int kProdSmem = kBwdStages * kStageBytes + kUnionBytes + kMaxBiasCols * 4;
+constexpr int kProdSmem = kBwdStages * kStageBytes + kUnionBytes + kMegaBiasCols * 4;
 constexpr int kConsSmem = kBwdStages * kCStageBytes;
 constexpr int kMegaSmem = (kProdSmem > kConsSmem ? kProdSmem : kConsSmem) + 1024 + 512;
 

@@ -41,8 +41,11 @@ def test_abi_version_and_workspace_arithmetic():
     big = lib.rnnt_fused_workspace_bytes(32, 500, 100, 1024, 1024)
     assert 0 < small < big < 1 << 30
     # unsupported shapes are reported, not silently accepted
-    assert lib.rnnt_fused_workspace_bytes(4, 200, 50, 4096, 512) == 0
-    assert b"V=4096" in lib.rnnt_last_error()
+    assert lib.rnnt_fused_workspace_bytes(4, 200, 50, 8192, 512) > 0            # word-piece vocabularies up to 8192
+    assert lib.rnnt_fused_workspace_bytes(4, 200, 50, 8193, 512) == 0
+    assert b"V=8193" in lib.rnnt_last_error()
+    assert lib.rnnt_fused_workspace_bytes(4, 200, 4095, 29, 512) > 0            # up to 4096 lattice columns
+    assert lib.rnnt_fused_workspace_bytes(4, 200, 4096, 29, 512) == 0
     assert lib.rnnt_fused_workspace_bytes(4, 200, 50, 29, 20) == 0
     assert lib.rnnt_lattice_workspace_bytes(4, 200, 50) > 0
 
