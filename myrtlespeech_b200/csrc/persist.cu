@@ -181,25 +181,23 @@ __device__ __forceinline__ void hgen_tile(const TileInfo& ti, const __nv_bfloat1
       if (dt + 1 < nt && dt + 1 < dt1)
         fnext = __ldg(reinterpret_cast<const uint4*>(f + (static_cast<size_t>(ti.b) * Tmax + ti.t0 + dt + 1) * H) + cv);
       __nv_bfloat16* orow = dst + static_cast<size_t>(dt * kTU) * H + cv * 8;
-      if (dt < nt) {
-        const uint32_t w[4] = {fq.x, fq.y, fq.z, fq.w};
-        float fv[8];
+      // Branch-free: every (frame, position) evaluates its eight tanh and rows outside the lattice are zeroed by a
+      // select.  With a branch per label position the MUFU chains of neighbouring positions cannot overlap across the
+      // reconvergence points: 12.3 k instead of 8.7 k cycles per 128 x 512 tile (scripts/micro/hgen_rate.cu).
+      const bool row_ok = dt < nt;
+      const uint32_t w[4] = {fq.x, fq.y, fq.z, fq.w};
+      float fv[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { fv[2 * e] = bf16lo(w[e]); fv[2 * e + 1] = bf16hi(w[e]); }
+      for (int e = 0; e < 4; ++e) { fv[2 * e] = bf16lo(w[e]); fv[2 * e + 1] = bf16hi(w[e]); }
 #pragma unroll
-        for (int du = 0; du < kTU; ++du) {
-          uint4 o = zero;
-          if (du < nu) {
-            o.x = pack_bf16x2(tanh_approx(fv[0] + gv[du][0]), tanh_approx(fv[1] + gv[du][1]));
-            o.y = pack_bf16x2(tanh_approx(fv[2] + gv[du][2]), tanh_approx(fv[3] + gv[du][3]));
-            o.z = pack_bf16x2(tanh_approx(fv[4] + gv[du][4]), tanh_approx(fv[5] + gv[du][5]));
-            o.w = pack_bf16x2(tanh_approx(fv[6] + gv[du][6]), tanh_approx(fv[7] + gv[du][7]));
-          }
-          st_cg_u4(orow + static_cast<size_t>(du) * H, o);
-        }
-      } else {
-#pragma unroll
-        for (int du = 0; du < kTU; ++du) st_cg_u4(orow + static_cast<size_t>(du) * H, zero);
+      for (int du = 0; du < kTU; ++du) {
+        uint4 o;
+        o.x = pack_bf16x2(tanh_approx(fv[0] + gv[du][0]), tanh_approx(fv[1] + gv[du][1]));
+        o.y = pack_bf16x2(tanh_approx(fv[2] + gv[du][2]), tanh_approx(fv[3] + gv[du][3]));
+        o.z = pack_bf16x2(tanh_approx(fv[4] + gv[du][4]), tanh_approx(fv[5] + gv[du][5]));
+        o.w = pack_bf16x2(tanh_approx(fv[6] + gv[du][6]), tanh_approx(fv[7] + gv[du][7]));
+        if (!(row_ok && du < nu)) o = zero;
+        st_cg_u4(orow + static_cast<size_t>(du) * H, o);
       }
       fq = fnext;
     }
@@ -541,6 +539,53 @@ __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.
 
 constexpr int kMegaThreads = 512;  // 16 warps, roles above (warps 8, 9 idle)
 
+// ---- dh-pass reductions in registers -------------------------------------------------------------------
+// A producer epilogue warp holds 32 tile rows: lane = 8 * (frame & 3) + label position.  df sums a column over
+// the 8 label positions of a frame (lane bits 0..2), dg over the frames (lane bits 3, 4 inside the warp, then over
+// the four warps of the set through shared memory).  Both run as halving butterflies: in each step a lane keeps
+// half of its columns, sends the other half to its partner and adds what it receives, so 32 columns take
+// 16 + 8 + 4 shuffles instead of 32 x 3 and every lane ends up owning a distinct, contiguous group of columns.
+// (The first design staged a 128 x 64 fp32 tile per set in shared memory and reduced it with two CTA-set barriers
+// per 64 columns: 9.7 k cycles per 256-column chunk, the bound of the V = 29 workload's backward pass.)
+__device__ __forceinline__ float shfl_xor_f(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// out[0..4): columns 4 * (lane & 7) .. + 3, summed over the 8 lanes of this lane's frame
+__device__ __forceinline__ void reduce_over_positions(const float (&v)[32], int lane, float (&out)[4]) {
+  float a[16], b[8];
+  const bool h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float keep = h4 ? v[16 + i] : v[i], send = h4 ? v[i] : v[16 + i];
+    a[i] = keep + shfl_xor_f(send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = h2 ? a[8 + i] : a[i], send = h2 ? a[i] : a[8 + i];
+    b[i] = keep + shfl_xor_f(send, 2);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h1 ? b[4 + i] : b[i], send = h1 ? b[i] : b[4 + i];
+    out[i] = keep + shfl_xor_f(send, 1);
+  }
+}
+
+// out[0..8): columns 8 * (lane >> 3) .. + 7, summed over the 4 frames this warp holds for this lane's label position
+__device__ __forceinline__ void reduce_over_frames(const float (&v)[32], int lane, float (&out)[8]) {
+  float a[16];
+  const bool h16 = lane & 16, h8 = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float keep = h16 ? v[16 + i] : v[i], send = h16 ? v[i] : v[16 + i];
+    a[i] = keep + shfl_xor_f(send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = h8 ? a[8 + i] : a[i], send = h8 ? a[i] : a[8 + i];
+    out[i] = keep + shfl_xor_f(send, 8);
+  }
+}
+
 __global__ void __launch_bounds__(kMegaThreads, 1)
 bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_wt,
@@ -740,7 +785,6 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       const uint32_t set_bar = half ? 3u : 1u;
       uint8_t* set_base = uni + half * (kBM * kDhPitch * 4);   // this set's fp32 dh tile; its dz staging lives inside
       uint8_t* slice0 = set_base + wi * 8192;                  // this warp's two 32-row x 128-byte staging slices
-      float* tile_s = reinterpret_cast<float*>(set_base);
       const int ncols_v = p.n_chunks_v * p.nc_v;
       for (int c = half * kEpiThreads + et; c < ncols_v; c += 2 * kEpiThreads)
         sbias[c] = (c < p.V) ? (p.bias ? p.bias[c] * kLog2e : 0.0f) : -INFINITY;
@@ -748,9 +792,6 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       // dz boxes (64 columns) of a chunk owned by this warp: 2*half + {0, 1}, as far as the chunk reaches
       int n_my_box = (p.nc_v + 63) / 64 - 2 * half;
       n_my_box = n_my_box < 0 ? 0 : (n_my_box > 2 ? 2 : n_my_box);
-      const int n_sub = (p.nc_h + 63) / 64;
-      int n_my_sub = n_sub - 2 * half;
-      n_my_sub = n_my_sub < 0 ? 0 : (n_my_sub > 2 ? 2 : n_my_sub);
 
       int gc = 0, it = 0;
 #ifdef RNNT_PROFILE
@@ -884,80 +925,47 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           }
         }
 
-        // ---- dh pass: set `half` reduces 64-column sub-chunks {2*half, 2*half + 1} of every chunk ----
+        // ---- dh pass: set `half` owns the 32-column groups g = 4*half .. 4*half + 3 of every 256-column chunk ----
         {
           named_bar_sync(set_bar, kEpiThreads);  // every warp of the set is done with its dz staging (TMA reads finished)
           const __nv_bfloat16* hrow = p.h_ring + (static_cast<size_t>(ring_row) + r) * p.H;
-          const int total_sub = p.n_chunks_h * n_my_sub;
-          auto load_h = [&](int s_idx, uint4 (&hv)[8]) {
-            const int jj = s_idx / n_my_sub, ss = 2 * half + (s_idx - jj * n_my_sub);
-#pragma unroll
-            for (int gg = 0; gg < 2; ++gg) {
-              const int g = ss * 2 + gg;
-              const int c0 = jj * p.nc_h + g * 32;
-              const uint4* hp = reinterpret_cast<const uint4*>(hrow + c0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                hv[gg * 4 + q] = (g * 32 < p.nc_h && c0 + 8 * q < p.H && !(p.dbg & 512)) ? ld_ca_u4(hp + q) : make_uint4(0, 0, 0, 0);
-            }
+          // partial dg sums of the set's four warps: [group 4][quad 4][label position 8][32 columns] fp32 = 16 KB, the
+          // eight 16-byte chunks of a row XOR-swizzled with the label position (conflict-free 128-bit accesses)
+          const uint32_t part_s = smem_u32(set_base);
+          const int dtl = lane >> 3;                       // frame inside this warp's four
+          const bool t_ok = !ghost && (ti.t0 + dt < ti.T);
+          auto groups_of = [&](int jj) {                   // 32-column groups of chunk jj this set owns (uniform in the set)
+            int lim = p.nc_h < p.H - jj * p.nc_h ? p.nc_h : p.H - jj * p.nc_h;   // columns of the chunk that exist
+            int n = (lim - 128 * half + 31) / 32;
+            return n < 0 ? 0 : (n > 4 ? 4 : n);
           };
-          uint4 hcur[8];
-          if (total_sub > 0) load_h(0, hcur);
-          int s_idx = 0;
+          auto load_h = [&](int jj, int gi, uint4 (&hv)[4]) {
+            const int c0 = jj * p.nc_h + (4 * half + gi) * 32;
+            const uint4* hp = reinterpret_cast<const uint4*>(hrow + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hv[q] = (c0 + 8 * q < p.H) ? ld_ca_u4(hp + q) : make_uint4(0, 0, 0, 0);
+          };
+          uint4 hcur[4];
+          if (groups_of(0) > 0) load_h(0, 0, hcur);
           for (int j = 0; j < p.n_chunks_h; ++j, ++gc) {
             const int buf = gc & 1;
+            const int n_g = groups_of(j);
             mbar_wait(&tfull_bar[buf], (gc >> 1) & 1);
             tc_fence_after();
 #ifdef RNNT_PROFILE
             const long long eh_t0 = clock64();
 #endif
-            if (n_my_sub == 0) {
+            if (n_g == 0) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive_even_cta(&tempty_bar[buf]);
             }
-            for (int q2 = 0; q2 < n_my_sub; ++q2, ++s_idx) {
-              const int sub = 2 * half + q2;
-              uint4 hnext[8];
-              if (s_idx + 1 < total_sub) {
-                load_h(s_idx + 1, hnext);
-              } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) hnext[q] = make_uint4(0, 0, 0, 0);
-              }
-              {
-                const uint32_t trow = smem_u32(tile_s) + (r * kDhPitch) * 4;
-#pragma unroll
-                for (int gg = 0; gg < 2; ++gg) {
-                  const int g = sub * 2 + gg;
-                  const int c0 = j * p.nc_h + g * 32;
-                  if (g * 32 < p.nc_h && c0 < p.H && !(p.dbg & 128)) {
-                    uint32_t raw[32];
-                    tmem_ld32(lane_taddr + buf * kNCmax + g * 32, raw);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                      const uint4 hq = hcur[gg * 4 + q];
-                      const uint32_t w[4] = {hq.x, hq.y, hq.z, hq.w};
-                      float o[8];
-#pragma unroll
-                      for (int e = 0; e < 4; ++e) {
-                        const float h0 = bf16lo(w[e]), h1 = bf16hi(w[e]);
-                        const float d0 = __uint_as_float(raw[8 * q + 2 * e]);
-                        const float d1 = __uint_as_float(raw[8 * q + 2 * e + 1]);
-                        o[2 * e] = fmaf(-h0 * h0, d0, d0);
-                        o[2 * e + 1] = fmaf(-h1 * h1, d1, d1);
-                      }
-                      sts128f(trow + (gg * 32 + 8 * q) * 4, o[0], o[1], o[2], o[3]);
-                      sts128f(trow + (gg * 32 + 8 * q + 4) * 4, o[4], o[5], o[6], o[7]);
-                    }
-                  } else if (!(p.dbg & 128)) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) sts128f(trow + (gg * 32 + 4 * i) * 4, 0.f, 0.f, 0.f, 0.f);
-                  }
-                }
-              }
-              if (q2 == n_my_sub - 1) {
+            for (int gi = 0; gi < n_g; ++gi) {
+              const int c0 = j * p.nc_h + (4 * half + gi) * 32;
+              uint32_t raw[32];
+              tmem_ld32(lane_taddr + buf * kNCmax + (4 * half + gi) * 32, raw);
+              tmem_ld_wait();
+              if (gi == n_g - 1) {   // the accumulator buffer is free as soon as this set's last group is in registers
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_even_cta(&tempty_bar[buf]);
@@ -965,41 +973,64 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 ep_hold_dh += clock64() - eh_t0;
 #endif
               }
-              named_bar_sync(set_bar, kEpiThreads);  // the set's dpre tile (128 rows x 64 columns) is complete
-              const int c4 = et & 15;
-              const int colbase = j * p.nc_h + sub * 64 + 4 * c4;
-              if (!ghost && !(p.dbg & 64) && sub * 64 + 4 * c4 < p.nc_h && colbase < p.H) {
-                const uint32_t tcol = smem_u32(tile_s) + 16 * c4;
+              uint4 hnext[4];
+              if (gi + 1 < n_g) {
+                load_h(j, gi + 1, hnext);
+              } else if (j + 1 < p.n_chunks_h && groups_of(j + 1) > 0) {
+                load_h(j + 1, 0, hnext);
+              } else {
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {  // df: sum over the 8 label positions of frame a
-                  const int a = (et >> 4) + 8 * k;
-                  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 4; ++q) hnext[q] = make_uint4(0, 0, 0, 0);
+              }
+              float v[32];
 #pragma unroll
-                  for (int c = 0; c < kTU; ++c) {
-                    const float4 v = lds128f(tcol + (a * kTU + c) * (kDhPitch * 4));
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                  }
-                  if (ti.t0 + a < ti.T)
-                    red_add_v4_f32(p.df + (static_cast<size_t>(ti.b) * p.L.Tmax + ti.t0 + a) * p.H + colbase, acc.x,
-                                   acc.y, acc.z, acc.w);
-                }
-                {  // dg: sum over the 16 frames of label position c
-                  const int c = et >> 4;
-                  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t w[4] = {hcur[q].x, hcur[q].y, hcur[q].z, hcur[q].w};
 #pragma unroll
-                  for (int a = 0; a < kTT; ++a) {
-                    const float4 v = lds128f(tcol + (a * kTU + c) * (kDhPitch * 4));
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                  }
-                  if (ti.u0 + c <= ti.U)
-                    red_add_v4_f32(p.dg + (static_cast<size_t>(ti.b) * p.L.U1max + ti.u0 + c) * p.H + colbase, acc.x,
-                                   acc.y, acc.z, acc.w);
+                for (int e = 0; e < 4; ++e) {
+                  const float h0 = bf16lo(w[e]), h1 = bf16hi(w[e]);
+                  const float d0 = __uint_as_float(raw[8 * q + 2 * e]);
+                  const float d1 = __uint_as_float(raw[8 * q + 2 * e + 1]);
+                  v[8 * q + 2 * e] = fmaf(-h0 * h0, d0, d0);
+                  v[8 * q + 2 * e + 1] = fmaf(-h1 * h1, d1, d1);
                 }
               }
-              named_bar_sync(set_bar, kEpiThreads);  // tile consumed: it may be rewritten (next sub / next tile's staging)
+              {  // df: this lane ends up with columns c0 + 4*du .. + 3 of its own frame, summed over the label positions
+                float o[4];
+                reduce_over_positions(v, lane, o);
+                if (t_ok && c0 + 4 * du < p.H)
+                  red_add_v4_f32(p.df + (static_cast<size_t>(ti.b) * p.L.Tmax + ti.t0 + dt) * p.H + c0 + 4 * du, o[0], o[1], o[2], o[3]);
+              }
+              {  // dg: columns c0 + 8*dtl .. + 7 of this lane's label position, summed over the warp's four frames
+                float o[8];
+                reduce_over_frames(v, lane, o);
+                const uint32_t prow = part_s + (((gi * 4 + quad) * 8 + du) << 7);
+                sts128f(prow + (((2 * dtl) ^ du) << 4), o[0], o[1], o[2], o[3]);
+                sts128f(prow + (((2 * dtl + 1) ^ du) << 4), o[4], o[5], o[6], o[7]);
+              }
 #pragma unroll
-              for (int q = 0; q < 8; ++q) hcur[q] = hnext[q];
+              for (int q = 0; q < 4; ++q) hcur[q] = hnext[q];
             }
+            named_bar_sync(set_bar, kEpiThreads);  // the four warps' partial sums of this chunk are in shared memory
+            if (!ghost) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int o = et + kEpiThreads * k;          // (group, label position, 4-column chunk)
+                const int gi = o >> 6, pu = (o >> 3) & 7, ch = o & 7;
+                const int col = j * p.nc_h + (4 * half + gi) * 32 + 4 * ch;
+                if (gi < n_g && col < p.H && ti.u0 + pu <= ti.U) {
+                  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                  for (int qd = 0; qd < 4; ++qd) {
+                    const float4 x = lds128f(part_s + (((gi * 4 + qd) * 8 + pu) << 7) + ((ch ^ pu) << 4));
+                    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                  }
+                  red_add_v4_f32(p.dg + (static_cast<size_t>(ti.b) * p.L.U1max + ti.u0 + pu) * p.H + col, acc.x, acc.y, acc.z,
+                                 acc.w);
+                }
+              }
+            }
+            named_bar_sync(set_bar, kEpiThreads);  // partial sums consumed: the buffer may be rewritten
 #ifdef RNNT_PROFILE
             ep_tot_dh += clock64() - eh_t0;
 #endif

@@ -1,0 +1,7 @@
+#!/bin/bash
+timeout 120 scripts/micro/hgen_rate > gpurun_out/r2_hgen_rate.log 2>&1; cat gpurun_out/r2_hgen_rate.log
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_gpu_hypothesis.py -x -q > gpurun_out/r2_pytest_gpu3.log 2>&1; tail -4 gpurun_out/r2_pytest_gpu3.log
+for w in target c2 c3; do python bench.py --workload $w --steps 30 --warmup 10 --no-cpu-baseline --no-decode 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('$w', d['ms_per_step'], d['value'], {k:v['ms_per_step'] for k,v in d['kernels'].items()}, d['roofline']['frac'], d['clocks']['sm_mhz'])
+"; done
