@@ -150,7 +150,7 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
   p.C = p.n_out * p.KG;
   p.P = kMaxPersistCtas / 2 - p.C;
   p.NS = g_ring_slots;
-  p.mega_ok = p.C <= 40 && p.P >= 1 && p.Vp <= 2048;   // 8 V chunks / 2048 bias columns in the mega-kernel
+  p.mega_ok = p.C <= 40 && p.P >= 1 && p.Vp <= 4096;   // 16 V chunks / 4096 bias columns in the mega-kernel
   p.o_hring = p.o_dzring = p.o_flags = 0;
   if (p.mega_ok) {
     p.o_hring = take(2 * static_cast<size_t>(p.P) * kMaxRingSlots * 2 * kTileRows * H);

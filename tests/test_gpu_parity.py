@@ -149,7 +149,9 @@ def test_ring_wraparound_many_tiles():
 @pytest.mark.parametrize("shape", [
     # B, T, U, V, H: role splits of the backward mega-kernel other than the 8-block x 3-group one
     (2, 20, 5, 2048, 64),     # 8 V-blocks x 1 H-block (the widest vocabulary the backward mega-kernel takes)
-    (2, 12, 4, 5000, 64),     # word-piece vocabulary beyond 2048: 20 V chunks, second partly filled; per-slab backward
+    (2, 20, 5, 4096, 64),     # 16 V-blocks x 1 H-block: the widest vocabulary the backward mega-kernel takes (one K-group)
+    (1, 24, 6, 3000, 512),    # 12 dW blocks, 12 V chunks with a partly filled last one, in the mega-kernel
+    (2, 12, 4, 5000, 64),     # word-piece vocabulary beyond 4096: 20 V chunks; per-slab backward
     (1, 9, 3, 8192, 128),     # the largest supported vocabulary
     (2, 20, 5, 64, 1536),     # 1 V-block x 3 H-blocks, odd number of dW blocks (no consumer sharing)
     (1, 9, 3, 2048, 3072),    # 48 dW blocks: more consumers than the split allows -> per-slab kernels
