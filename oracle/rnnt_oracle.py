@@ -331,6 +331,96 @@ def greedy_decode(
     return out, float(min_margin)
 
 
+def verify_greedy_transcript(
+    f_b: np.ndarray,
+    n_frames: int,
+    W: np.ndarray,
+    bias: Optional[np.ndarray],
+    pred_step: Callable[[Optional[int], object], Tuple[np.ndarray, object]],
+    blank: int,
+    max_symbols_per_step: int,
+    hyp: Sequence[int],
+    eps: float,
+    faithful: bool = False,
+) -> Tuple[bool, float, int]:
+    """Checks a transcript produced by ANOTHER implementation of the greedy search, decision by decision.
+
+    The prediction-network state depends only on the symbols emitted so far, so the logits of every decision are a
+    function of (frame t, symbols emitted i): ``z(t, i) = W . tanh(f[t] + g_i) + b`` with ``g_i`` the prediction output
+    after ``hyp[:i]``.  The decoder's run is a path through that (t, i) lattice: "blank" moves to ``(t + 1, i)``,
+    "emit hyp[i]" to ``(t, i + 1)`` (at most ``max_symbols_per_step`` emissions per frame, then the frame advances).
+    The transcript is accepted if such a path from ``(0, 0)`` to ``(n_frames, len(hyp))`` exists on which every action
+    taken is an eps-argmax of its ``z`` (within ``eps`` of the best logit) -- i.e. every decision of the other
+    implementation is one this oracle would make too, up to a logit difference of ``eps``.  Unlike comparing whole
+    transcripts this verifies EVERY symbol, also after a near-tie went the other way.
+
+    Returns ``(accepted, regret, n_ties)``: ``regret`` is the smallest eps that would have been needed (the minimum
+    over accepting paths of the largest ``max(z) - z[action]`` along the path; ``inf`` if none exists) and ``n_ties``
+    the number of lattice cells visited in which both actions were within ``eps``.
+    """
+    f_b = np.asarray(f_b, dtype=np.float64)
+    W = np.asarray(W, dtype=np.float64)
+    b_ = np.zeros(W.shape[0]) if bias is None else np.asarray(bias, dtype=np.float64)
+    hyp = [int(k) for k in hyp]
+    S = int(max_symbols_per_step)
+    # prediction outputs after every prefix of the transcript
+    g_list = []
+    g, state = pred_step(None, None)
+    g_list.append(np.asarray(g, dtype=np.float64))
+    for k in hyp:
+        g, state = pred_step(k, state)
+        g_list.append(np.asarray(g, dtype=np.float64))
+    cache = {}
+
+    def gaps(t, i):
+        """(max(z) - z[blank], max(z) - z[hyp[i]] or inf)"""
+        if (t, i) not in cache:
+            x = f_b[t] + g_list[i]
+            if faithful:
+                x = x.astype(np.float32).astype(np.float64)
+            h = np.tanh(x)
+            if faithful:
+                h = bf16_round(h)
+            z = W @ h + b_
+            m = float(z.max())
+            cache[(t, i)] = (m - float(z[blank]), m - float(z[hyp[i]]) if i < len(hyp) else np.inf)
+        return cache[(t, i)]
+
+    # best[(t, i, n)] = smallest achievable "largest regret so far" on a path reaching that state (Dijkstra-like sweep in
+    # topological order: t + i is monotone along every transition)
+    import heapq
+    start = (0, 0, 0)
+    best = {start: 0.0}
+    heap = [(0, 0.0, start)]          # ordered by t + i, then regret
+    n_ties = 0
+    seen = set()
+    result = np.inf
+    while heap:
+        _, r, st = heapq.heappop(heap)
+        if st in seen or r > best.get(st, np.inf):
+            continue
+        seen.add(st)
+        t, i, n = st
+        if t == n_frames:
+            if i == len(hyp):
+                result = min(result, r)
+            continue
+        gb, ge = gaps(t, i)
+        if gb <= eps and ge <= eps:
+            n_ties += 1
+        moves = []
+        if gb <= eps:
+            moves.append(((t + 1, i, 0), max(r, gb)))
+        if ge <= eps and i < len(hyp) and hyp[i] != blank:
+            nxt = (t + 1, i + 1, 0) if n + 1 == S else (t, i + 1, n + 1)
+            moves.append((nxt, max(r, ge)))
+        for nxt, rr in moves:
+            if rr < best.get(nxt, np.inf):
+                best[nxt] = rr
+                heapq.heappush(heap, (nxt[0] + nxt[1], rr, nxt))
+    return bool(np.isfinite(result)), float(result), n_ties
+
+
 # --------------------------------------------------------------------------- #
 # prediction network step (embedding + single-layer LSTM + projection)
 # --------------------------------------------------------------------------- #

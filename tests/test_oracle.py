@@ -228,3 +228,25 @@ def test_gru_pred_step_matches_torch_gru():
         got, state = step(lab, state)
         want, hx = pred.step(None if lab is None else torch.tensor([lab]), hx, 1, torch.device("cpu"))
         np.testing.assert_allclose(got, want[0].detach().numpy(), rtol=1e-10, atol=1e-12)
+
+
+def test_verify_greedy_transcript_accepts_the_greedy_path_and_rejects_others():
+    """The decision-by-decision checker used for long GPU decodes: the oracle's own transcript is accepted with zero
+    regret; a changed, a truncated and an extended transcript are rejected."""
+    rng = np.random.default_rng(0)
+    V, H, Hp, E, T, S = 12, 16, 8, 4, 25, 3
+    step = O.lstm_pred_step(rng.normal(size=(V + 1, E)), [rng.normal(size=(4 * Hp, E))], [rng.normal(size=(4 * Hp, Hp))],
+                            [None], [None], rng.normal(size=(H, Hp)), None, faithful=True)
+    f = rng.normal(size=(1, T, H)); W = rng.normal(size=(V, H))
+    hyps, _ = O.greedy_decode(f, [T], W, None, step, V - 1, S, faithful=True)
+    hyp = hyps[0]
+    assert len(hyp) > 10
+    ok, regret, ties = O.verify_greedy_transcript(f[0], T, W, None, step, V - 1, S, hyp, 1e-9, faithful=True)
+    assert ok and regret == 0.0 and ties == 0
+    bad = list(hyp); bad[3] = (bad[3] + 1) % (V - 1)
+    for other in (bad, hyp[:-1], hyp + [1]):
+        ok, regret, _ = O.verify_greedy_transcript(f[0], T, W, None, step, V - 1, S, other, 1e-2, faithful=True)
+        assert not ok and regret == float("inf")
+    # a huge eps accepts anything that fits the lattice, and reports how far from greedy it was
+    ok, regret, _ = O.verify_greedy_transcript(f[0], T, W, None, step, V - 1, S, bad, 1e3, faithful=True)
+    assert ok and regret > 1e-2
