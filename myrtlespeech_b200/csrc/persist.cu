@@ -670,10 +670,12 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
               if ((p.dbg & 256) && n_issued >= kStages) {
                 if (leader && elect_one()) mbar_arrive(&full_bar[s]);
               } else if (elect_one()) {
-                if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * (kAStage + bv_bytes));
+                const bool skip_b = p.dbg & 16384;    // bring-up: no W loads (timing only)
+                if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * (kAStage + (skip_b ? 0u : bv_bytes)));
                 const uint32_t sa = sbase + s * kStageBytes;
                 tma_load_2d_pair_a(sa, &tm_h, &full_bar[s], k * kBK, ring_row);
-                if (lockstep)
+                if (skip_b) {
+                } else if (lockstep)
                   tma_load_2d_pair_mcast(sa + kAStage + cpair * (bv_bytes >> 1), &tm_w, &full_bar[s], k * kBK,
                                          j * p.nc_v + static_cast<int>(rank) * ncv_half + static_cast<int>(cpair) * (ncv_half >> 1),
                                          twin_mask);
@@ -700,10 +702,12 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
               if ((p.dbg & 256) && n_issued >= kStages) {
                 if (leader && elect_one()) mbar_arrive(&full_bar[s]);
               } else if (elect_one()) {
-                if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * (kAStage + bh_bytes));
+                const bool skip_b = p.dbg & 16384;
+                if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * (kAStage + (skip_b ? 0u : bh_bytes)));
                 const uint32_t sa = sbase + s * kStageBytes;
                 tma_load_2d_pair_a(sa, &tm_dz, &full_bar[s], k * kBK, ring_row);
-                if (lockstep)
+                if (skip_b) {
+                } else if (lockstep)
                   tma_load_2d_pair_mcast(sa + kAStage + cpair * (bh_bytes >> 1), &tm_wt, &full_bar[s], k * kBK,
                                          j * p.nc_h + static_cast<int>(rank) * nch_half + static_cast<int>(cpair) * (nch_half >> 1),
                                          twin_mask);
@@ -879,7 +883,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
               __syncwarp();
               if (lane == 0) {
                 const int col = j * p.nc_v + bcol;
-                if (col < p.Vp) tma_store_2d(&tm_dz_st, sl, col, ring_row + quad * 32);
+                if (col < p.Vp && !(p.dbg & 2048)) tma_store_2d(&tm_dz_st, sl, col, ring_row + quad * 32);
                 tma_store_commit();
               }
             }
@@ -943,7 +947,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             const int c0 = jj * p.nc_h + (4 * half + gi) * 32;
             const uint4* hp = reinterpret_cast<const uint4*>(hrow + c0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) hv[q] = (c0 + 8 * q < p.H) ? ld_ca_u4(hp + q) : make_uint4(0, 0, 0, 0);
+            for (int q = 0; q < 4; ++q) hv[q] = (c0 + 8 * q < p.H && !(p.dbg & 512)) ? ld_ca_u4(hp + q) : make_uint4(0, 0, 0, 0);
           };
           uint4 hcur[4];
           if (groups_of(0) > 0) load_h(0, 0, hcur);
@@ -998,7 +1002,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
               {  // df: this lane ends up with columns c0 + 4*du .. + 3 of its own frame, summed over the label positions
                 float o[4];
                 reduce_over_positions(v, lane, o);
-                if (t_ok && c0 + 4 * du < p.H)
+                if (t_ok && c0 + 4 * du < p.H && !(p.dbg & 4096))
                   red_add_v4_f32(p.df + (static_cast<size_t>(ti.b) * p.L.Tmax + ti.t0 + dt) * p.H + c0 + 4 * du, o[0], o[1], o[2], o[3]);
               }
               {  // dg: columns c0 + 8*dtl .. + 7 of this lane's label position, summed over the warp's four frames
@@ -1018,7 +1022,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 const int o = et + kEpiThreads * k;          // (group, label position, 4-column chunk)
                 const int gi = o >> 6, pu = (o >> 3) & 7, ch = o & 7;
                 const int col = j * p.nc_h + (4 * half + gi) * 32 + 4 * ch;
-                if (gi < n_g && col < p.H && ti.u0 + pu <= ti.U) {
+                if (gi < n_g && col < p.H && ti.u0 + pu <= ti.U && !(p.dbg & 4096)) {
                   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                   for (int qd = 0; qd < 4; ++qd) {
@@ -1065,7 +1069,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         } else {
           ti.b = 0; ti.t0 = 0; ti.u0 = 0; ti.T = 0; ti.U = -1;             // ghost half: all-zero rows
         }
-        hgen_tile(ti, p.f, p.g, p.h_ring + static_cast<size_t>(ring_row) * p.H, p.H, p.L.Tmax, p.L.U1max, ht);
+        // bring-up: dbg & 1024 skips the producers' hgen work (timing only: what would moving hgen off the producers buy?)
+        if (!(p.dbg & 1024) || use == 0)
+          hgen_tile(ti, p.f, p.g, p.h_ring + static_cast<size_t>(ring_row) * p.H, p.H, p.L.Tmax, p.L.U1max, ht);
         __threadfence();
         fence_proxy_async_global();
         mbar_arrive(&hfull_bar[slot]);
@@ -1101,7 +1107,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         const int row0 = (pp * p.NS + slot) * 2 * kBM;
         for (int kb = 0; kb < 4; ++kb) {
           { PCNT_BEGIN(a); mbar_wait(&empty_bar[s], ph ^ 1); PCNT_END(a, w_empty); }
-          if ((p.dbg & 256) && n_issued >= kStages) {
+          if (((p.dbg & 256) && n_issued >= kStages) || (p.dbg & 8192)) {   // bring-up: no consumer loads (timing only)
             if (leader && elect_one()) mbar_arrive(&full_bar[s]);
           } else if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(&full_bar[s], stage_tx);
