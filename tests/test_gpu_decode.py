@@ -320,7 +320,8 @@ def test_fused_stacked_lstm_decode_matches_oracle(seed, B, T, V, H, Hp, E, S, la
 
 
 def test_packed_prediction_weights_are_cached_and_invalidated():
-    """The decoder repacks the prediction network only when a parameter changed in place (optimiser step, load)."""
+    """The decoder repacks the prediction network only when a parameter changed -- in place (optimiser step, load) or
+    behind the version counter's back (``.data`` writes): the cache is validated by content on every call."""
     joint, pred, f, lens = _lstm_case(3, 5, 23, 40, 64, 64, 32)
     model = RNNT(torch.nn.Identity(), pred, joint).cuda()
     dec = RNNTGreedyDecoder(39, model, max_symbols_per_step=2)
@@ -337,5 +338,16 @@ def test_packed_prediction_weights_are_cached_and_invalidated():
         assert len(calls) == 2
         want, margins = _oracle_transcripts(joint, pred, f, lens, 39, 2)
         assert [g for g, m in zip(c, margins) if m > MARGIN] == [w for w, m in zip(want, margins) if m > MARGIN]
+        # updates that bypass the version counter (EMA swaps, legacy optimisers writing .data) are caught by the content check
+        v0 = pred.proj.weight._version
+        pred.proj.weight.data.mul_(0.5)
+        pred.rnn.weight_hh_l0.data = pred.rnn.weight_hh_l0.data * 1.5
+        assert pred.proj.weight._version == v0
+        d = dec(f.cuda(), lens)
+        assert len(calls) == 3
+        want, margins = _oracle_transcripts(joint, pred, f, lens, 39, 2)
+        assert [g for g, m in zip(d, margins) if m > MARGIN] == [w for w, m in zip(want, margins) if m > MARGIN]
+        dec.invalidate_cache()
+        assert dec(f.cuda(), lens) == d and len(calls) == 4
     finally:
         D._pack_lstm_prediction = orig
