@@ -29,6 +29,7 @@ int g_ring_slots = 2;
 int g_kg_override = 0;   // bring-up: K-groups of dW consumers in the backward mega-kernel (0 = plan's choice)
 int g_cluster = 2;      // forward kernel: CTAs per cluster; 4 = two CTA pairs sharing W through TMA multicast
                         // (measured slower: only 132 of the 148 SMs can host 4-clusters)
+int g_fwd_hgen_warps = 0;  // 0 = by shape; 4 / 8 force the forward kernel's number of hgen warps
 int g_cluster_bwd = 2;  // backward mega-kernel: 4-clusters cannot all be co-resident (132 of 148 SMs), so pairs
 
 int fail(int code, const char* fmt, ...) {
@@ -379,6 +380,7 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "mega_cooperative")) set_bwd_mega_cooperative(value);  // 0: plain launch (ncu cannot replay cooperative launches)
   if (!strcmp(key, "cluster") && (value == 2 || value == 4)) g_cluster = value;
   if (!strcmp(key, "cluster_bwd") && (value == 2 || value == 4)) g_cluster_bwd = value;
+  if (!strcmp(key, "fwd_hgen_warps")) g_fwd_hgen_warps = value;
   if (!strcmp(key, "ring_slots") && value >= 2 && value <= 4) g_ring_slots = value;
   if (!strcmp(key, "reset_launches")) for (int i = 0; i < K_NCLASS; ++i) g_launches[i] = 0;
 }
@@ -462,7 +464,10 @@ int rnnt_fused_forward(const void* f, const void* g, const void* W, const float*
 
   if (g_path == 1) {
     const int csize = (nc % 32 == 0 && g_cluster == 4) ? 4 : 2;
-    int n_ctas = max_ctas_fwd_persist(csize);
+    // One accumulator chunk per tile (V <= 256): the MMAs of a tile are shorter than its tanh pass, so the pass is bound by
+    // the hgen warps -- run eight of them (two per scheduler) instead of four.
+    const int hgen_warps = (g_fwd_hgen_warps == 4 || g_fwd_hgen_warps == 8) ? g_fwd_hgen_warps : ((V + nc - 1) / nc == 1 ? 8 : 4);
+    int n_ctas = max_ctas_fwd_persist(csize, hgen_warps);
     if (n_ctas > kMaxPersistCtas) n_ctas = kMaxPersistCtas;
     n_ctas = n_ctas / csize * csize;
     const int n_ptiles = (n_tiles + 1) / 2;
@@ -476,7 +481,7 @@ int rnnt_fused_forward(const void* f, const void* g, const void* W, const float*
       if (rc) return rc;
     }
     FwdPArgs pa{};
-    pa.L = L; pa.dbg = get_gemm_dbg(); pa.csize = csize; pa.n_tiles_total = n_tiles; pa.V = V; pa.H = H; pa.nc = nc; pa.n_chunks = (V + nc - 1) / nc;
+    pa.L = L; pa.dbg = get_gemm_dbg(); pa.csize = csize; pa.hgen_warps = hgen_warps; pa.n_tiles_total = n_tiles; pa.V = V; pa.H = H; pa.nc = nc; pa.n_chunks = (V + nc - 1) / nc;
     pa.k_blocks = (H + 63) / 64; pa.blank = blank; pa.Umax = d.Umax;
     pa.f = static_cast<const __nv_bfloat16*>(f); pa.g = static_cast<const __nv_bfloat16*>(g);
     pa.hscratch = w.at<__nv_bfloat16>(p.o_hs);

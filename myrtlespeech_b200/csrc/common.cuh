@@ -50,6 +50,30 @@ __device__ __forceinline__ TileInfo decode_tile(const Lattice& L, int gtile) {
   return ti;
 }
 
+// The persistent kernels walk tiles in increasing order, so the utterance of the next tile is the current one or a later
+// one: a cursor that remembers (b, prefix[b], prefix[b+1], T_b, U_b) replaces the binary search -- five dependent loads
+// that miss L1 on every tile, because the gpu-scope fences of the producer warps invalidate it -- by loads only where an
+// utterance boundary is crossed (measured: 3.5 k of the 12 k cycles the V = 29 forward pass spent per tile).
+struct TileCursor {
+  int b, lo, hi, T, U;
+  __device__ __forceinline__ void init(const Lattice& L) {
+    b = 0; lo = 0; hi = L.tile_prefix[1]; T = L.f_lens[0]; U = L.y_lens[0];
+  }
+  __device__ __forceinline__ TileInfo at(const Lattice& L, int gtile) {
+    if (gtile >= hi && b + 1 < L.B) {
+      do { ++b; lo = hi; hi = L.tile_prefix[b + 1]; } while (gtile >= hi && b + 1 < L.B);
+      T = L.f_lens[b]; U = L.y_lens[b];
+    }
+    TileInfo ti;
+    ti.b = b; ti.T = T; ti.U = U;
+    const int n_ub = (U + 1 + kTU - 1) / kTU;
+    const int local = gtile - lo;
+    ti.t0 = (local / n_ub) * kTT;
+    ti.u0 = (local % n_ub) * kTU;
+    return ti;
+  }
+};
+
 __device__ __forceinline__ size_t diag_index(const Lattice& L, int b, int t, int u) {
   return (static_cast<size_t>(b) * L.D + (t + u)) * L.U1max + u;
 }

@@ -101,6 +101,7 @@ struct FwdPArgs {
   Lattice L;
   int dbg;
   int csize;                  // CTAs per cluster: 2 (one CTA pair) or 4 (two pairs, W multicast)
+  int hgen_warps;             // 4, or 8 for narrow vocabularies (the pass is bound by the tanh evaluations)
   int n_tiles_total;
   int V, H;
   int nc, n_chunks, k_blocks;
@@ -118,7 +119,7 @@ struct FwdPArgs {
 void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
                         cudaStream_t s);
 int smem_bytes_fwd_persist();
-int max_ctas_fwd_persist(int csize);
+int max_ctas_fwd_persist(int csize, int hgen_warps = 4);
 int read_persist_prof(unsigned long long* out, int n);
 int get_gemm_dbg();
 

@@ -27,7 +27,6 @@ constexpr int kNCmax = 256;
 constexpr int kAStage = kBM * kBK * 2;
 constexpr int kBStage = (kNCmax / 2) * kBK * 2;
 constexpr int kStageBytes = kAStage + kBStage;
-constexpr int kPThreads = 320;
 constexpr int kEpiThreads = 128;
 constexpr int kHgenThreads = 128;
 constexpr int kTmemCols = 512;
@@ -39,7 +38,6 @@ constexpr int kMegaBiasCols = 4096;     // backward mega-kernel: 16 KB bias tabl
 //   forward: 0..3 epilogue, 4..7 hgen, 8 TMA, 9 MMA (+ TMEM alloc)
 //   mega   : 0..3 epilogue set 0, 4..7 epilogue set 1, 10, 11, 14, 15 hgen (sub-partitions 2 and 3 only, away from
 //            the two issuer warps), 12 TMA, 13 MMA (+ TMEM alloc); 8, 9 idle
-constexpr int kFwdTmaWarp = 8, kFwdMmaWarp = 9;
 constexpr int kMegaTmaWarp = 12, kMegaMmaWarp = 13;
 
 // bring-up profiling (gemm_dbg & 4): per-CTA wait-cycle counters of the last persistent launch
@@ -145,6 +143,7 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // Called by the 128 hgen threads (ht = 0..127).  A thread owns one 8-column vector and a range of frames: with
 // H >= 1024 every thread walks all 16 frames of its vectors cv = ht, ht + 128, ...; with fewer vectors than threads
 // (H < 1024) the frames are split between thread groups so that all four warps (one per MUFU unit) stay busy.
+template <int kNT = kHgenThreads>
 __device__ __forceinline__ void hgen_tile(const TileInfo& ti, const __nv_bfloat16* __restrict__ f,
                                           const __nv_bfloat16* __restrict__ g, __nv_bfloat16* dst, int H, int Tmax,
                                           int U1max, int ht) {
@@ -152,9 +151,9 @@ __device__ __forceinline__ void hgen_tile(const TileInfo& ti, const __nv_bfloat1
   int nt = ti.T - ti.t0; nt = nt < 0 ? 0 : (nt > kTT ? kTT : nt);
   int nu = ti.U + 1 - ti.u0; nu = nu < 0 ? 0 : (nu > kTU ? kTU : nu);
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  int cv0 = ht, cv_step = kHgenThreads, dt0 = 0, dt1 = kTT;
-  if (nvec < kHgenThreads) {
-    const int n_groups = kHgenThreads / nvec;                 // >= 1
+  int cv0 = ht, cv_step = kNT, dt0 = 0, dt1 = kTT;
+  if (nvec < kNT) {
+    const int n_groups = kNT / nvec;                 // >= 1
     const int fpg = (kTT + n_groups - 1) / n_groups;          // frames per group
     const int grp = ht / nvec;
     cv0 = ht - grp * nvec;
@@ -249,9 +248,14 @@ __device__ __forceinline__ void issue_chunk(RingState& st, const uint64_t ad0, c
 constexpr int kFwdStages = 6;
 constexpr int kFwdSmem = kFwdStages * kStageBytes + kMaxBiasCols * 4 + 1024 + 256;
 
-__global__ void __launch_bounds__(kPThreads, 1)
+// kHW = number of hgen warps: 4 (one per MUFU unit; the tensor-bound shapes) or 8 (narrow vocabularies, where the
+// forward pass is bound by the tanh pass: two warps per scheduler overlap each other's MUFU latency and stores).
+template <int kHW>
+__global__ void __launch_bounds__((6 + kHW) * 32, 1)
 fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const FwdPArgs p) {
   constexpr int kStages = kFwdStages;
+  constexpr int kFwdTmaWarp = 4 + kHW, kFwdMmaWarp = 5 + kHW;
+  constexpr int kHT = kHW * 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -288,7 +292,7 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], quad ? 2 : 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8);
-      mbar_init(&hfull_bar[i], kHgenThreads); mbar_init(&hempty_bar[i], 1);
+      mbar_init(&hfull_bar[i], kHT); mbar_init(&hempty_bar[i], 1);
     }
     fence_barrier_init();
   }
@@ -393,10 +397,12 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
     int gc = 0;
     long long busy = 0;
+    TileCursor cur;
+    cur.init(p.L);
     for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += n_pairs, pf += n_pairs) {
       const int tile = 2 * pt + static_cast<int>(rank);
       const bool ghost = tile >= p.n_tiles_total;
-      const TileInfo ti = decode_tile(p.L, ghost ? p.n_tiles_total - 1 : tile);
+      const TileInfo ti = cur.at(p.L, ghost ? p.n_tiles_total - 1 : tile);
       const int t = ti.t0 + dt, u = ti.u0 + du;
       const bool valid = !ghost && (t < ti.T) && (u <= ti.U);
       const size_t grow = static_cast<size_t>(tile) * kBM + r;
@@ -453,14 +459,16 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     __nv_bfloat16* my_scratch = p.hscratch + static_cast<size_t>(a_row0) * p.H;
     int it = 0;
     long long busy = 0;
+    TileCursor cur;
+    cur.init(p.L);
     for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += n_pairs, pf += n_pairs, ++it) {
       const int hb = it & 1;
       const int tile = 2 * pt + static_cast<int>(rank);
       mbar_wait(&hempty_bar[hb], ((it >> 1) & 1) ^ 1);
       PCNT_BEGIN(h);
       if (tile < p.n_tiles_total) {
-        const TileInfo ti = decode_tile(p.L, tile);
-        hgen_tile(ti, p.f, p.g, my_scratch + static_cast<size_t>(hb) * kBM * p.H, p.H, p.L.Tmax, p.L.U1max, ht);
+        const TileInfo ti = cur.at(p.L, tile);
+        hgen_tile<kHT>(ti, p.f, p.g, my_scratch + static_cast<size_t>(hb) * kBM * p.H, p.H, p.L.Tmax, p.L.U1max, ht);
       }
       __threadfence();
       fence_proxy_async_global();
@@ -801,12 +809,14 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 #ifdef RNNT_PROFILE
       long long ep_hold_dz = 0, ep_tot_dz = 0, ep_hold_dh = 0, ep_tot_dh = 0;
 #endif
+      TileCursor cur;
+      cur.init(p.L);
       for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P, ++it) {
         const int slot = it % p.NS, use = it / p.NS;
         const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
         const int tile = 2 * pt + static_cast<int>(rank);
         const bool ghost = tile >= p.n_tiles_total;
-        const TileInfo ti = decode_tile(p.L, ghost ? p.n_tiles_total - 1 : tile);
+        const TileInfo ti = cur.at(p.L, ghost ? p.n_tiles_total - 1 : tile);
         const int t = ti.t0 + dt, u = ti.u0 + du;
         const bool valid = !ghost && (t < ti.T) && (u <= ti.U);
         const size_t grow = static_cast<size_t>(tile) * kBM + r;
@@ -1054,6 +1064,8 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       // ------------------------------- hgen (warps 10, 11, 14, 15) --------------------
       const int ht = ((warp & 1) + ((warp >> 2) & 1) * 2) * 32 + lane;   // 10->0, 11->1, 14->2, 15->3
       int it = 0;
+      TileCursor cur;
+      cur.init(p.L);
       for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P, ++it) {
         const int slot = it % p.NS, use = it / p.NS;
         const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
@@ -1065,7 +1077,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         }
         TileInfo ti;
         if (tile < p.n_tiles_total) {
-          ti = decode_tile(p.L, tile);
+          ti = cur.at(p.L, tile);
         } else {
           ti.b = 0; ti.t0 = 0; ti.u0 = 0; ti.T = 0; ti.U = -1;             // ghost half: all-zero rows
         }
@@ -1238,23 +1250,27 @@ int smem_bytes_fwd_persist() { return kFwdSmem; }
 
 // Largest number of CTAs of the forward kernel that are co-resident for this cluster size (GPCs whose SM count is
 // not a multiple of the cluster size strand SMs: 148 CTAs fit as pairs, only 132 as 4-clusters on this B200).
-int max_ctas_fwd_persist(int csize) {
+template <int kHW>
+static int max_ctas_fwd_persist_t(int csize) {
   static int cache[kMaxDevices][5] = {};
   int* cached = cache[current_device()];
   if (cached[csize]) return cached[csize];
-  cudaFuncSetAttribute(fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+  cudaFuncSetAttribute(fwd_persist_kernel<kHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(csize * 64);
-  cfg.blockDim = dim3(kPThreads);
+  cfg.blockDim = dim3((6 + kHW) * 32);
   cfg.dynamicSmemBytes = kFwdSmem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, fwd_persist_kernel, &cfg) != cudaSuccess || n <= 0) n = 148 / csize;
+  if (cudaOccupancyMaxActiveClusters(&n, fwd_persist_kernel<kHW>, &cfg) != cudaSuccess || n <= 0) n = 148 / csize;
   cached[csize] = n * csize;
   return cached[csize];
+}
+int max_ctas_fwd_persist(int csize, int hgen_warps) {
+  return hgen_warps == 8 ? max_ctas_fwd_persist_t<8>(csize) : max_ctas_fwd_persist_t<4>(csize);
 }
 int read_persist_prof(unsigned long long* out, int n) {
   if (n > 2 * 160 * 8) n = 2 * 160 * 8;
@@ -1264,23 +1280,29 @@ int read_persist_prof(unsigned long long* out, int n) {
   return n;
 }
 
-void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
-                        cudaStream_t s) {
+template <int kHW>
+static void launch_fwd_persist_t(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
+                                 cudaStream_t s) {
   static bool configured[kMaxDevices] = {};
   if (bool& c = configured[current_device()]; !c) {
-    cudaFuncSetAttribute(fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+    cudaFuncSetAttribute(fwd_persist_kernel<kHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
     c = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_ctas);
-  cfg.blockDim = dim3(kPThreads);
+  cfg.blockDim = dim3((6 + kHW) * 32);
   cfg.dynamicSmemBytes = kFwdSmem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = a.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, fwd_persist_kernel, tm_hscratch, tm_w, a);
+  cudaLaunchKernelEx(&cfg, fwd_persist_kernel<kHW>, tm_hscratch, tm_w, a);
+}
+void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
+                        cudaStream_t s) {
+  if (a.hgen_warps == 8) launch_fwd_persist_t<8>(tm_hscratch, tm_w, a, n_ctas, s);
+  else launch_fwd_persist_t<4>(tm_hscratch, tm_w, a, n_ctas, s);
 }
 
 
