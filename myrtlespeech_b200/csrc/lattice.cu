@@ -23,9 +23,12 @@ namespace {
 // (ex2.approx / lg2.approx, absolute error ~1e-7).  Per cell and step this costs three DADDs and two conversions
 // on top of the fp32 chain.
 __device__ __forceinline__ double logaddexp_d(double a, double b) {
-  const double m = fmax(a, b);
-  const float diff = static_cast<float>(fmin(a, b) - m);   // <= 0; -inf-like operands give 0 or a huge negative
-  return m + static_cast<double>(kLn2 * lg2f(1.0f + ex2f(diff * kLog2e)));
+  // branch-free: the sign of a - b picks the maximum, |a - b| goes through the fp32 correction.  Both operands are
+  // always finite (log(0) is the large negative kNegD, never -inf), so a - b is never NaN.
+  const double d = a - b;
+  const double m = __double2hiint(d) < 0 ? b : a;
+  const float ad = static_cast<float>(fabs(d));             // huge differences become +inf: ex2(-inf) = 0
+  return m + static_cast<double>(kLn2 * lg2f(1.0f + ex2f(-ad * kLog2e)));
 }
 
 constexpr double kNegD = -1.0e30;
@@ -33,6 +36,12 @@ constexpr double kNegD = -1.0e30;
 // NC = lattice columns per thread (column u = threadIdx.x + k * blockDim.x): 1 up to 1024 columns, 2 / 4 beyond.
 // kMaxT = launch bound: the usual U + 1 <= 256 gets a 256-thread variant whose register budget holds the prefetch
 // registers without spills.
+//
+// The dependent chain of one wavefront step is  neighbour value (shared memory) -> logaddexp -> two adds -> shared
+// memory -> barrier.  Everything else is kept off it and free of branches: the arc log-probabilities are prefetched
+// kPrefetch diagonals ahead with "no arc" already encoded as kNeg (cells outside the lattice, the last frame's blank
+// arc, the last column's label arc), stores are predicated, and the two special cells (alpha's final cell, beta's
+// first) are handled by selects.
 template <int NC, int kMaxT>
 __global__ void __launch_bounds__(kMaxT, 1)
 lattice_alpha_beta_kernel(Lattice L, const float* __restrict__ lpb, const float* __restrict__ lpl,
@@ -44,11 +53,12 @@ lattice_alpha_beta_kernel(Lattice L, const float* __restrict__ lpb, const float*
   const bool is_beta = blockIdx.y == 1;
   const int T = L.f_lens[b];
   const int U = L.y_lens[b];
+  const int U1 = L.U1max;
   const int ncols = NC * blockDim.x;
   const int stride = ncols + 2;
   double* s0 = sbuf;
   double* s1 = sbuf + stride;
-  const size_t base = static_cast<size_t>(b) * L.D * L.U1max;
+  const size_t base = static_cast<size_t>(b) * L.D * U1;
   const float* pb = lpb + base;
   const float* pl = lpl + base;
   const int dlast = T - 1 + U;
@@ -56,38 +66,33 @@ lattice_alpha_beta_kernel(Lattice L, const float* __restrict__ lpb, const float*
   for (int i = threadIdx.x; i < 2 * stride; i += blockDim.x) sbuf[i] = kNegD;
   __syncthreads();
 
+  // arc log-probabilities of cell (t = d - u, u) on diagonal d: eb = blank arc (t,u) -> (t+1,u), el = label arc
+  // (t,u) -> (t,u+1); kNeg where the cell or the arc does not exist
+  auto fetch = [&](int d, int u, float& eb, float& el) {
+    const int t = d - u;
+    const bool ok = u <= U && t >= 0 && t < T && d >= 0 && d <= dlast;
+    eb = (ok && t + 1 < T) ? pb[static_cast<size_t>(d) * U1 + u] : kNeg;
+    el = (ok && u < U) ? pl[static_cast<size_t>(d) * U1 + u] : kNeg;
+  };
+
   float cb[NC][kPrefetch], cl[NC][kPrefetch];
 
   if (!is_beta) {
     double* out = alpha + base;
     // s?[u+1] holds the label-arc contribution arriving at column u+1; s?[0] stays kNeg.
-    double a_cur[NC];
+    double a_cur[NC], a_fin = 0.0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) a_cur[c] = (c == 0 && threadIdx.x == 0) ? 0.0 : kNegD;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int u = threadIdx.x + c * blockDim.x;
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int i = 0; i < kPrefetch; ++i) {
-        const int d = i, t = d - u;
-        const bool ok = u <= U && t >= 0 && t < T && d <= dlast;
-        cb[c][i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-        cl[c][i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-      }
-    }
+      for (int i = 0; i < kPrefetch; ++i) fetch(i, threadIdx.x + c * blockDim.x, cb[c][i], cl[c][i]);
     for (int d0 = 0; d0 <= dlast; d0 += kPrefetch) {
       float nb[NC][kPrefetch], nl[NC][kPrefetch];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const int u = threadIdx.x + c * blockDim.x;
+      for (int c = 0; c < NC; ++c)
 #pragma unroll
-        for (int i = 0; i < kPrefetch; ++i) {
-          const int d = d0 + kPrefetch + i, t = d - u;
-          const bool ok = u <= U && t >= 0 && t < T && d <= dlast;
-          nb[c][i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-          nl[c][i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-        }
-      }
+        for (int i = 0; i < kPrefetch; ++i) fetch(d0 + kPrefetch + i, threadIdx.x + c * blockDim.x, nb[c][i], nl[c][i]);
 #pragma unroll
       for (int i = 0; i < kPrefetch; ++i) {
         const int d = d0 + i;
@@ -98,20 +103,10 @@ lattice_alpha_beta_kernel(Lattice L, const float* __restrict__ lpb, const float*
           for (int c = 0; c < NC; ++c) {
             const int u = threadIdx.x + c * blockDim.x;
             const int t = d - u;
-            const bool valid = u <= U && t >= 0 && t < T;
-            double ol = kNegD;
-            ob[c] = kNegD;
-            if (valid) {
-              out[static_cast<size_t>(d) * L.U1max + u] = a_cur[c];
-              if (t + 1 < T) ob[c] = a_cur[c] + static_cast<double>(cb[c][i]);
-              if (u < U) ol = a_cur[c] + static_cast<double>(cl[c][i]);
-              if (t == T - 1 && u == U) {
-                const double lnp = a_cur[c] + static_cast<double>(cb[c][i]);
-                loss[b] = static_cast<float>(-lnp);
-                lnp64[b] = lnp;
-              }
-            }
-            sw[u + 1] = ol;
+            if (u <= U && t >= 0 && t < T) out[static_cast<size_t>(d) * U1 + u] = a_cur[c];   // predicated store
+            a_fin = (d == dlast && u == U) ? a_cur[c] : a_fin;
+            ob[c] = a_cur[c] + static_cast<double>(cb[c][i]);
+            sw[u + 1] = a_cur[c] + static_cast<double>(cl[c][i]);
           }
           __syncthreads();
 #pragma unroll
@@ -123,36 +118,32 @@ lattice_alpha_beta_kernel(Lattice L, const float* __restrict__ lpb, const float*
 #pragma unroll
         for (int i = 0; i < kPrefetch; ++i) { cb[c][i] = nb[c][i]; cl[c][i] = nl[c][i]; }
     }
+    // ln P = alpha[T-1, U] + lp_blank[T-1, U]: the thread that owns column U
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (static_cast<int>(threadIdx.x + c * blockDim.x) == U) {
+        const double lnp = a_fin + static_cast<double>(pb[static_cast<size_t>(dlast) * U1 + U]);
+        loss[b] = static_cast<float>(-lnp);
+        lnp64[b] = lnp;
+      }
+    }
   } else {
     double* out = beta + base;
     // s?[u] holds beta of the previous (d+1) diagonal at column u.
     double b_prev[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) b_prev[c] = kNegD;
+    const double lpb_final = static_cast<double>(pb[static_cast<size_t>(dlast) * U1 + U]);   // beta[T-1, U]
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int u = threadIdx.x + c * blockDim.x;
+    for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int i = 0; i < kPrefetch; ++i) {
-        const int d = dlast - i, t = d - u;
-        const bool ok = u <= U && t >= 0 && t < T && d >= 0;
-        cb[c][i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-        cl[c][i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-      }
-    }
+      for (int i = 0; i < kPrefetch; ++i) fetch(dlast - i, threadIdx.x + c * blockDim.x, cb[c][i], cl[c][i]);
     for (int d0 = dlast; d0 >= 0; d0 -= kPrefetch) {
       float nb[NC][kPrefetch], nl[NC][kPrefetch];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const int u = threadIdx.x + c * blockDim.x;
+      for (int c = 0; c < NC; ++c)
 #pragma unroll
-        for (int i = 0; i < kPrefetch; ++i) {
-          const int d = d0 - kPrefetch - i, t = d - u;
-          const bool ok = u <= U && t >= 0 && t < T && d >= 0;
-          nb[c][i] = ok ? pb[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-          nl[c][i] = (ok && u < U) ? pl[static_cast<size_t>(d) * L.U1max + u] : kNeg;
-        }
-      }
+        for (int i = 0; i < kPrefetch; ++i) fetch(d0 - kPrefetch - i, threadIdx.x + c * blockDim.x, nb[c][i], nl[c][i]);
 #pragma unroll
       for (int i = 0; i < kPrefetch; ++i) {
         const int d = d0 - i;
@@ -163,19 +154,9 @@ lattice_alpha_beta_kernel(Lattice L, const float* __restrict__ lpb, const float*
           for (int c = 0; c < NC; ++c) {
             const int u = threadIdx.x + c * blockDim.x;
             const int t = d - u;
-            const bool valid = u <= U && t >= 0 && t < T;
-            double bv = kNegD;
-            if (valid) {
-              if (t == T - 1 && u == U) {
-                bv = static_cast<double>(cb[c][i]);
-              } else {
-                const double x = (t + 1 < T) ? b_prev[c] + static_cast<double>(cb[c][i]) : kNegD;
-                const double y = (u < U) ? sr[u + 1] + static_cast<double>(cl[c][i]) : kNegD;
-                bv = logaddexp_d(x, y);
-              }
-              out[static_cast<size_t>(d) * L.U1max + u] = bv;
-              if (d == 0) lnp_beta[b] = static_cast<float>(bv);
-            }
+            double bv = logaddexp_d(b_prev[c] + static_cast<double>(cb[c][i]), sr[u + 1] + static_cast<double>(cl[c][i]));
+            bv = (d == dlast && u == U) ? lpb_final : bv;
+            if (u <= U && t >= 0 && t < T) out[static_cast<size_t>(d) * U1 + u] = bv;            // predicated store
             b_prev[c] = bv;
             sw[u] = bv;
           }
@@ -187,6 +168,7 @@ lattice_alpha_beta_kernel(Lattice L, const float* __restrict__ lpb, const float*
 #pragma unroll
         for (int i = 0; i < kPrefetch; ++i) { cb[c][i] = nb[c][i]; cl[c][i] = nl[c][i]; }
     }
+    if (threadIdx.x == 0) lnp_beta[b] = static_cast<float>(b_prev[0]);   // beta[0, 0]
   }
 }
 
