@@ -168,6 +168,8 @@ long long rnnt_debug_get(const char* key);                /* "launches": kernels
 int rnnt_debug_kernel_times(double* ms, long long* count, int n);
 /* Bring-up: %globaltimer stamps (8 per CTA) of the last tcgen05 GEMM launch made with gemm_dbg & 4. */
 int rnnt_debug_read_prof(unsigned long long* out, int n);
+/* RNNT_PROFILE builds: per-CTA phase cycles of the mega-kernel's dh epilogue (8 values per CTA), optionally reset. */
+int rnnt_debug_read_prof3(unsigned long long* out, int n, int reset);
 /* Cluster decode with rnnt_debug_set("decode_prof", 1): SM cycles the epilogue of cluster 0 / rank 0 spent per stage,
  * summed over steps (out[0..9)), and the step count (out[9]). */
 int rnnt_debug_decode_prof(unsigned long long* out, int n);

@@ -37,6 +37,7 @@ SIGNATURES = {
     "rnnt_debug_get": (ctypes.c_longlong, [ctypes.c_char_p]),
     "rnnt_debug_kernel_times": (_c_int, [_vp, _vp, _c_int]),
     "rnnt_debug_read_prof": (_c_int, [_vp, _c_int]),
+    "rnnt_debug_read_prof3": (_c_int, [_vp, _c_int, _c_int]),
     "rnnt_debug_decode_prof": (_c_int, [_vp, _c_int]),
 }
 

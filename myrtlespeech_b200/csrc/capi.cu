@@ -404,6 +404,8 @@ long long rnnt_debug_get(const char* key) {
 
 int rnnt_debug_decode_prof(unsigned long long* out, int n) { return read_decode_prof(out, n); }
 
+int rnnt_debug_read_prof3(unsigned long long* out, int n, int reset) { return read_persist_prof3(out, n, reset); }
+
 int rnnt_debug_read_prof(unsigned long long* out, int n) { return g_path == 1 ? read_persist_prof(out, n) : read_gemm_prof(out, n); }
 
 int rnnt_debug_kernel_times(double* ms, long long* count, int n) {

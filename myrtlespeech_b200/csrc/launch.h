@@ -121,6 +121,7 @@ void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w,
 int smem_bytes_fwd_persist();
 int max_ctas_fwd_persist(int csize, int hgen_warps = 4);
 int read_persist_prof(unsigned long long* out, int n);
+int read_persist_prof3(unsigned long long* out, int n, int reset);
 int get_gemm_dbg();
 
 struct BwdPArgs {

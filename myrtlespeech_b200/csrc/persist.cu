@@ -46,6 +46,7 @@ constexpr int kMegaTmaWarp = 12, kMegaMmaWarp = 13;
 //   [6] hgen busy cycles  [7] epilogue busy cycles (between tfull and tempty arrive)
 __device__ unsigned long long g_pprof[160 * 8];
 __device__ unsigned long long g_pprof2[160 * 8];   // second bank (RNNT_PROFILE builds): per-pass chunk issue cycles
+__device__ unsigned long long g_pprof3[160 * 8];   // third bank (RNNT_PROFILE builds): dh-epilogue phase cycles of warp 0, summed
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -961,11 +962,21 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           };
           uint4 hcur[4];
           if (groups_of(0) > 0) load_h(0, 0, hcur);
+#ifdef RNNT_PROFILE
+          long long q_tm = 0, q_math = 0, q_red = 0, q_b1 = 0, q_fin = 0, q_b2 = 0, q_wait = 0;
+#define QT(acc) do { const long long now_ = clock64(); acc += now_ - q_t; q_t = now_; } while (0)
+#else
+#define QT(acc) do { } while (0)
+#endif
           for (int j = 0; j < p.n_chunks_h; ++j, ++gc) {
             const int buf = gc & 1;
             const int n_g = groups_of(j);
+#ifdef RNNT_PROFILE
+            long long q_t = clock64();
+#endif
             mbar_wait(&tfull_bar[buf], (gc >> 1) & 1);
             tc_fence_after();
+            QT(q_wait);
 #ifdef RNNT_PROFILE
             const long long eh_t0 = clock64();
 #endif
@@ -979,6 +990,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
               uint32_t raw[32];
               tmem_ld32(lane_taddr + buf * kNCmax + (4 * half + gi) * 32, raw);
               tmem_ld_wait();
+              QT(q_tm);
               if (gi == n_g - 1) {   // the accumulator buffer is free as soon as this set's last group is in registers
                 tc_fence_before();
                 __syncwarp();
@@ -1009,6 +1021,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                   v[8 * q + 2 * e + 1] = fmaf(-h1 * h1, d1, d1);
                 }
               }
+              QT(q_math);
               {  // df: this lane ends up with columns c0 + 4*du .. + 3 of its own frame, summed over the label positions
                 float o[4];
                 reduce_over_positions(v, lane, o);
@@ -1024,8 +1037,10 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
               }
 #pragma unroll
               for (int q = 0; q < 4; ++q) hcur[q] = hnext[q];
+              QT(q_red);
             }
             named_bar_sync(set_bar, kEpiThreads);  // the four warps' partial sums of this chunk are in shared memory
+            QT(q_b1);
             if (!ghost) {
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
@@ -1044,13 +1059,21 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 }
               }
             }
+            QT(q_fin);
             named_bar_sync(set_bar, kEpiThreads);  // partial sums consumed: the buffer may be rewritten
+            QT(q_b2);
 #ifdef RNNT_PROFILE
             ep_tot_dh += clock64() - eh_t0;
 #endif
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&hfree_bar[slot]);
+#ifdef RNNT_PROFILE
+          if ((p.dbg & 4) && threadIdx.x == 0) {
+            unsigned long long* o = g_pprof3 + blockIdx.x * 8;
+            o[0] += q_wait; o[1] += q_tm; o[2] += q_math; o[3] += q_red; o[4] += q_b1; o[5] += q_fin; o[6] += q_b2; o[7] += p.n_chunks_h;
+          }
+#endif
         }
       }
 #ifdef RNNT_PROFILE
@@ -1271,6 +1294,12 @@ static int max_ctas_fwd_persist_t(int csize) {
 }
 int max_ctas_fwd_persist(int csize, int hgen_warps) {
   return hgen_warps == 8 ? max_ctas_fwd_persist_t<8>(csize) : max_ctas_fwd_persist_t<4>(csize);
+}
+int read_persist_prof3(unsigned long long* out, int n, int reset) {
+  if (n > 160 * 8) n = 160 * 8;
+  if (cudaMemcpyFromSymbol(out, g_pprof3, sizeof(unsigned long long) * n) != cudaSuccess) return -1;
+  if (reset) { static unsigned long long z[160 * 8] = {}; cudaMemcpyToSymbol(g_pprof3, z, sizeof(z)); }
+  return n;
 }
 int read_persist_prof(unsigned long long* out, int n) {
   if (n > 2 * 160 * 8) n = 2 * 160 * 8;
