@@ -509,6 +509,7 @@ constexpr int kDhPitch = 68;
 constexpr int kUnionBytes = 2 * kBM * kDhPitch * 4;  // dh fp32 tiles (69,632 B) >= dz staging (65,536 B)
 constexpr int kCStageBytes = 3 * 16384;
 constexpr int kMaxNS = 4;
+constexpr int kFlushEvery = 256;   // consumers flush their dW accumulators every 256 pair-tiles (65 k lattice rows)
 constexpr int kMaxVChunks = kMegaBiasCols / 256;   // 16 chunks of 256 vocabulary columns
 constexpr int kProdSmem = kBwdStages * kStageBytes + kUnionBytes + kMegaBiasCols * 4;
 constexpr int kConsSmem = kBwdStages * kCStageBytes;
@@ -635,8 +636,8 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     prefetch_tmap(&tm_h); prefetch_tmap(&tm_w); prefetch_tmap(&tm_dz);
     prefetch_tmap(&tm_wt); prefetch_tmap(&tm_dz_mn); prefetch_tmap(&tm_h_mn); prefetch_tmap(&tm_dz_st);
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], lockstep ? 2 : 1); }
-    // producers: 8 epilogue warps per CTA; consumers: 4 flush warps per CTA never arrive on tempty
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }
+    // producers: 8 epilogue warps per CTA; consumers: 4 flush warps per CTA (periodic flush of the dW accumulators)
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], is_producer ? 16 : 8); }
     for (int i = 0; i < kMaxNS; ++i) { mbar_init(&hfull_bar[i], kHgenThreads); mbar_init(&hfree_bar[i], 8); }
     for (int i = 0; i < kMaxVChunks; ++i) mbar_init(&dzr_bar[i], 8);
     fence_barrier_init();
@@ -1189,9 +1190,21 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         long long w_full = 0;
         const long long c_begin = clock64();
         const unsigned long long ns_begin = gtimer_ns();
+        int n_done = 0, n_flushed = 0;
         for (int pt = kg; pt < n_ptiles; pt += p.KG) {
           const int pp = pt % p.P, it = pt / p.P;
           unsigned* done_ptr = p.done + pp * p.NS + it % p.NS;
+          if (n_done > 0 && n_done % kFlushEvery == 0) {
+            // hand the accumulators to the flush warps and restart from zero: one fp32 accumulator per dW element for the
+            // whole step (1.6 M rows at the target shape) lost a decimal digit against the per-slab schedule
+            if (elect_one()) umma_commit_pair(&tfull_bar[0], pair_mask);
+            __syncwarp();
+            mbar_wait(&tempty_bar[0], n_flushed & 1);
+            tc_fence_after();
+            ++n_flushed;
+            acc = 0;
+          }
+          ++n_done;
           for (int kb = 0; kb < 4; ++kb) {
             if (!ready) { PCNT_BEGIN(a); mbar_wait_a(fb, ph); PCNT_END(a, w_full); }
             tc_fence_after();
@@ -1227,12 +1240,15 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         const int quad = warp & 3;
         const int r = quad * 32 + lane;
         const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-        mbar_wait(&tfull_bar[0], 0);
-        tc_fence_after();
         const int v = v0 + r;
         const int hbase = hn * 512;
         float* out = p.dW + static_cast<size_t>(v) * p.H + hbase;
         const int n_groups = two ? 16 : 8;
+        const int n_flushes = (n_mine + kFlushEvery - 1) / kFlushEvery;   // every kFlushEvery pair-tiles and at the end
+#pragma unroll 1
+        for (int fl = 0; fl < n_flushes; ++fl) {
+        mbar_wait(&tfull_bar[0], fl & 1);
+        tc_fence_after();
 #pragma unroll 1
         for (int g = 0; g < n_groups; ++g) {
           uint32_t raw[32];
@@ -1254,6 +1270,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           }
         }
         tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_even_cta(&tempty_bar[0]);   // the accumulators may be overwritten
+        }
       }
     }
   }

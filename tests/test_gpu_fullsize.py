@@ -11,8 +11,8 @@ Tolerances (``north_star``: "loss and gradients within 1e-3 relative in fp32-acc
 * ``rel``    = ||got - ref||_F / ||ref||_F   < 1e-3 for every output;
 * ``relmax`` = max|got - ref| / max|ref|     < the per-output bound in ``RELMAX``.
 
-Measured (round 2, both schedules): loss 1e-7, db 1e-6 .. 1e-5, dW 2e-5 (per-slab) / 2e-4 (persistent: one fp32 TMEM
-accumulator per dW block for the whole step), dg 2e-5 / relmax 8e-5, df 1.9e-4 / relmax 3.2e-3 .. 4.0e-3.
+Measured (round 2, both schedules): loss 1e-7, db 1e-6 .. 1e-5, dW 2e-5 (per-slab) / 3e-5 .. 4e-5 (persistent: the fp32 TMEM
+accumulators of a dW block are flushed every 256 pair-tiles), dg 2e-5 / relmax 8e-5, df 1.9e-4 / relmax 3.2e-3 .. 4.0e-3.
 
 Why ``relmax`` of df is allowed above 1e-3 -- the one bound that is not met element-wise.  The kernels evaluate
 ``h = bf16(tanh.approx.f32(f + g))``; the checker evaluates ``bf16(tanh(f + g))`` with a correctly rounded tanh.
@@ -41,7 +41,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-3
 #: element-wise bounds, max|got - ref| / max|ref| (see the module docstring for df / dg)
-RELMAX = {"loss": 1e-5, "df": 6e-3, "dg": 5e-4, "dW": 1e-3, "db": 1e-4}
+RELMAX = {"loss": 1e-5, "df": 6e-3, "dg": 5e-4, "dW": 3e-4, "db": 1e-4}
 
 CONFIGS = {
     # name: (B, T, U, V, H)
