@@ -160,7 +160,9 @@ int rnnt_debug_copy_stats(const void* workspace, int B, int Tmax, int Umax, int 
                           float* lp_label, float* c_blank, float* c_label, float* lnp_beta, void* stream);
 void rnnt_debug_set(const char* key, int value);          /* "slab_tiles", "time_kernels", "reset_launches",
                                                               "path" (1 persistent kernels, 0 per-slab kernels),
-                                                              "ring_slots" (2..4), "gemm_dbg" (bring-up switches) */
+                                                              "ring_slots" (2..4), "gemm_dbg" (bring-up switches),
+                                                              "prune" (-1: the backward pass walks every tile; default 0: only
+                                                              tiles with non-zero occupancy), "prune_log2_eps" (threshold 2^v) */
 long long rnnt_debug_get(const char* key);                /* "launches": kernels launched since the last reset */
 /* In "time_kernels" mode every kernel launch is bracketed by CUDA events on its stream; this call
  * synchronises, sums the durations per kernel class (hgen, joint_fwd, joint_dz, joint_dh, joint_dw,
@@ -168,6 +170,9 @@ long long rnnt_debug_get(const char* key);                /* "launches": kernels
 int rnnt_debug_kernel_times(double* ms, long long* count, int n);
 /* Bring-up: %globaltimer stamps (8 per CTA) of the last tcgen05 GEMM launch made with gemm_dbg & 4. */
 int rnnt_debug_read_prof(unsigned long long* out, int n);
+/* After rnnt_fused_backward on `workspace`: out2[0] = lattice tiles the backward pass walked (those with non-zero arc
+ * occupancy), out2[1] = tiles in the batch.  Synchronises the device. */
+int rnnt_debug_read_active_tiles(const void* workspace, int B, int Tmax, int Umax, int V, int H, int* out2);
 /* RNNT_PROFILE builds: per-CTA phase cycles of the mega-kernel's dh epilogue (8 values per CTA), optionally reset. */
 int rnnt_debug_read_prof3(unsigned long long* out, int n, int reset);
 /* Cluster decode with rnnt_debug_set("decode_prof", 1): SM cycles the epilogue of cluster 0 / rank 0 spent per stage,

@@ -38,6 +38,7 @@ SIGNATURES = {
     "rnnt_debug_kernel_times": (_c_int, [_vp, _vp, _c_int]),
     "rnnt_debug_read_prof": (_c_int, [_vp, _c_int]),
     "rnnt_debug_read_prof3": (_c_int, [_vp, _c_int, _c_int]),
+    "rnnt_debug_read_active_tiles": (_c_int, [_vp] + [_c_int] * 5 + [_vp]),
     "rnnt_debug_decode_prof": (_c_int, [_vp, _c_int]),
 }
 

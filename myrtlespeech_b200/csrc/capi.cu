@@ -29,6 +29,8 @@ int g_ring_slots = 2;
 int g_kg_override = 0;   // bring-up: K-groups of dW consumers in the backward mega-kernel (0 = plan's choice)
 int g_cluster = 2;      // forward kernel: CTAs per cluster; 4 = two CTA pairs sharing W through TMA multicast
                         // (measured slower: only 132 of the 148 SMs can host 4-clusters)
+int g_prune = 0;            // backward mega-kernel: >= 0 walks only tiles that carry occupancy; -1 = every tile
+int g_prune_log2_eps = -100000;  // occupancy threshold 2^v (default: exact zero only)
 int g_fwd_hgen_warps = 0;  // 0 = by shape; 4 / 8 force the forward kernel's number of hgen warps
 int g_cluster_bwd = 2;  // backward mega-kernel: 4-clusters cannot all be co-resident (132 of 148 SMs), so pairs
 
@@ -91,7 +93,7 @@ int sm_count() {
 struct Plan {
   int B, Tmax, Umax, U1, V, H, Vp, D;
   int max_tiles, slab_tiles;
-  size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_lnp64, o_wt, o_h, o_dz, o_hs, o_hring, o_dzring, o_flags;
+  size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_lnp64, o_wt, o_h, o_dz, o_hs, o_hring, o_dzring, o_flags, o_tflags, o_active, o_nactive;
   int mega_ok, n_vt, n_ht, n_out, KG, C, P, NS;
   size_t state_bytes, total;
 };
@@ -152,6 +154,9 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
   p.P = kMaxPersistCtas / 2 - p.C;
   p.NS = g_ring_slots;
   p.mega_ok = p.C <= 40 && p.P >= 1 && p.Vp <= 4096;   // 16 V chunks / 4096 bias columns in the mega-kernel
+  p.o_tflags = take(sizeof(int) * static_cast<size_t>(p.max_tiles));   // backward-pass tile list (lattice.cu)
+  p.o_active = take(sizeof(int) * static_cast<size_t>(p.max_tiles));
+  p.o_nactive = take(sizeof(int) * 4);
   p.o_hring = p.o_dzring = p.o_flags = 0;
   if (p.mega_ok) {
     p.o_hring = take(2 * static_cast<size_t>(p.P) * kMaxRingSlots * 2 * kTileRows * H);
@@ -381,6 +386,8 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "cluster") && (value == 2 || value == 4)) g_cluster = value;
   if (!strcmp(key, "cluster_bwd") && (value == 2 || value == 4)) g_cluster_bwd = value;
   if (!strcmp(key, "fwd_hgen_warps")) g_fwd_hgen_warps = value;
+  if (!strcmp(key, "prune")) g_prune = value;
+  if (!strcmp(key, "prune_log2_eps")) g_prune_log2_eps = value;
   if (!strcmp(key, "ring_slots") && value >= 2 && value <= 4) g_ring_slots = value;
   if (!strcmp(key, "reset_launches")) for (int i = 0; i < K_NCLASS; ++i) g_launches[i] = 0;
 }
@@ -403,6 +410,14 @@ long long rnnt_debug_get(const char* key) {
 }
 
 int rnnt_debug_decode_prof(unsigned long long* out, int n) { return read_decode_prof(out, n); }
+
+int rnnt_debug_read_active_tiles(const void* workspace, int B, int Tmax, int Umax, int V, int H, int* out2) {
+  if (check_dims(B, Tmax, Umax, V, H) != RNNT_OK) return RNNT_ERR_INVALID_ARGUMENT;
+  const Plan p = make_plan(B, Tmax, Umax, V, H);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out2, static_cast<const uint8_t*>(workspace) + p.o_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+  return RNNT_OK;
+}
 
 int rnnt_debug_read_prof3(unsigned long long* out, int n, int reset) { return read_persist_prof3(out, n, reset); }
 
@@ -561,6 +576,12 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
     BwdPArgs a{};
     a.L = L; a.dbg = get_gemm_dbg(); a.csize = csize; a.cons_share = (csize == 4 && p.n_vt % 2 == 0) ? 1 : 0;
     a.n_tiles_total = n_tiles; a.V = V; a.H = H; a.Vp = p.Vp;
+    if (g_prune >= 0) {   // walk only the tiles whose cells carry occupancy (exact for eps = 0, the default)
+      const float eps = g_prune_log2_eps <= -1000 ? 0.0f : exp2f(static_cast<float>(g_prune_log2_eps));
+      KLAUNCH(K_MISC, s, launch_tile_activity(L, w.at<float>(p.o_c1), w.at<float>(p.o_c2), grad_loss, eps, w.at<int>(p.o_tflags), s));
+      KLAUNCH(K_MISC, s, launch_compact_tiles(w.at<int>(p.o_tflags), n_tiles, w.at<int>(p.o_active), w.at<int>(p.o_nactive), s));
+      a.active_tiles = w.at<int>(p.o_active); a.n_active = w.at<int>(p.o_nactive);
+    }
     a.nc_v = nc_v; a.n_chunks_v = (V + nc_v - 1) / nc_v; a.kb_h = (H + 63) / 64;
     a.nc_h = nc_h; a.n_chunks_h = (H + nc_h - 1) / nc_h; a.kb_v = p.Vp / 64;
     a.blank = blank; a.Umax = d.Umax;

@@ -202,6 +202,77 @@ __global__ void lattice_coefs_kernel(Lattice L, const float* __restrict__ lpb, c
   }
 }
 
+// ---- which tiles does the backward pass need? ---------------------------------------------------------------------
+// d loss / d logits of a lattice cell is  c0 * softmax - [blank] c1 - [label] c2  with the arc occupancies c1, c2 and
+// c0 = c1 + c2: a tile whose 128 cells all have c0 == 0 -- the alignment never gets there: exp(alpha + beta - lnP)
+// underflows, as it does for a fifth of the lattice of a 500 x 101 utterance -- contributes exact zeros to every gradient,
+// so the backward pass walks the compacted list of the other tiles.  With eps > 0 tiles whose largest occupancy is below
+// eps are dropped too (off by default).
+__global__ void tile_activity_kernel(Lattice L, const float* __restrict__ c1, const float* __restrict__ c2,
+                                     const float* __restrict__ grad_loss, float eps, int* __restrict__ flags) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= L.n_tiles_total) return;
+  const TileInfo ti = decode_tile(L, warp);
+  float m = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kTileRows / 32; ++k) {
+    const int r = lane + 32 * k;
+    const int t = ti.t0 + (r >> 3), u = ti.u0 + (r & 7);
+    if (t < ti.T && u <= ti.U) {
+      const size_t i = diag_index(L, ti.b, t, u);
+      m = fmaxf(m, c1[i] + c2[i]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) flags[warp] = (m * fabsf(grad_loss[ti.b]) > eps) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+compact_tiles_kernel(const int* __restrict__ flags, int n_tiles, int* __restrict__ active, int* __restrict__ n_active) {
+  // one block; every thread scans kItems consecutive flags, so a batch of 13 k tiles takes a single pass
+  constexpr int kItems = 16;
+  __shared__ int warp_sums[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int start = 0; start < n_tiles; start += 1024 * kItems) {
+    const int i0 = start + threadIdx.x * kItems;
+    int f[kItems];
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) { f[k] = (i0 + k < n_tiles) ? flags[i0 + k] : 0; mine += f[k]; }
+    int incl = mine;                                    // inclusive scan of the per-thread counts inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int ws = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += v;
+      }
+      warp_sums[lane] = ws;                             // inclusive over the warps
+    }
+    __syncthreads();
+    int pos = base + (warp > 0 ? warp_sums[warp - 1] : 0) + incl - mine;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k)
+      if (f[k]) active[pos++] = i0 + k;
+    __syncthreads();
+    if (threadIdx.x == 0) base += warp_sums[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { n_active[0] = base; n_active[1] = n_tiles; }
+}
+
 // natural [B][Tmax][U1max] <-> diagonal [B][D][U1max] layout (only the explicit-logits entry point needs it)
 __global__ void nat_to_diag_kernel(Lattice L, const float* __restrict__ a_nat, const float* __restrict__ b_nat,
                                    float* __restrict__ a_diag, float* __restrict__ b_diag) {
@@ -229,6 +300,16 @@ __global__ void diag_to_nat_kernel(Lattice L, const float* __restrict__ a_diag, 
 }
 
 }  // namespace
+
+void launch_tile_activity(const Lattice& L, const float* c1, const float* c2, const float* grad_loss, float eps, int* flags,
+                          cudaStream_t s) {
+  if (L.n_tiles_total <= 0) return;
+  const int blocks = (L.n_tiles_total * 32 + 255) / 256;
+  tile_activity_kernel<<<blocks, 256, 0, s>>>(L, c1, c2, grad_loss, eps, flags);
+}
+void launch_compact_tiles(const int* flags, int n_tiles, int* active, int* n_active, cudaStream_t s) {
+  compact_tiles_kernel<<<1, 1024, 0, s>>>(flags, n_tiles, active, n_active);
+}
 
 void launch_nat_to_diag(const Lattice& L, const float* a_nat, const float* b_nat, float* a_diag, float* b_diag,
                         cudaStream_t s) {

@@ -31,6 +31,12 @@ void launch_lattice_coefs(const Lattice& L, const float* lpb, const float* lpl, 
 
 void launch_nat_to_diag(const Lattice& L, const float* a_nat, const float* b_nat, float* a_diag, float* b_diag,
                         cudaStream_t s);
+// Backward-pass tile list: flags[tile] = (max over the tile's cells of (c1 + c2) * |grad_loss[b]|) > eps, then the
+// indices of the flagged tiles in increasing order (active) and their number (n_active[0]; n_active[1] = n_tiles).
+void launch_tile_activity(const Lattice& L, const float* c1, const float* c2, const float* grad_loss, float eps, int* flags,
+                          cudaStream_t s);
+void launch_compact_tiles(const int* flags, int n_tiles, int* active, int* n_active, cudaStream_t s);
+
 void launch_diag_to_nat(const Lattice& L, const float* a_diag, const float* b_diag, float* a_nat, float* b_nat,
                         cudaStream_t s);
 
@@ -130,6 +136,8 @@ struct BwdPArgs {
   int csize;                   // CTAs per cluster (2 or 4)
   int cons_share;              // 4-clusters of consumers share their h boxes (n_vt even)
   int n_tiles_total;
+  const int* active_tiles;     // compacted list of the tiles that carry occupancy (device), or null = all tiles
+  const int* n_active;         // its length (device)
   int V, H, Vp;
   int nc_v, n_chunks_v, kb_h;  // dz pass: N chunks over V, k-blocks over H
   int nc_h, n_chunks_h, kb_v;  // dh pass: N chunks over H, k-blocks over Vp

@@ -624,7 +624,10 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   const uint32_t cpair = rank4 >> 1;          // pair inside the cluster
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
-  const int n_ptiles = (p.n_tiles_total + 1) >> 1;
+  // Tiles of the backward pass: all of them, or the compacted list of tiles whose lattice cells carry any occupancy
+  // (tile_activity / compact_tiles below); the count then lives in device memory.
+  const int n_tiles = p.active_tiles ? *p.n_active : p.n_tiles_total;
+  const int n_ptiles = (n_tiles + 1) >> 1;
   const bool is_producer = pair < p.P;
   const bool lockstep = p.csize == 4 && (is_producer || p.cons_share);   // this cluster's two pairs run in lockstep
   const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * cpair));
@@ -816,9 +819,11 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P, ++it) {
         const int slot = it % p.NS, use = it / p.NS;
         const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
-        const int tile = 2 * pt + static_cast<int>(rank);
-        const bool ghost = tile >= p.n_tiles_total;
-        const TileInfo ti = cur.at(p.L, ghost ? p.n_tiles_total - 1 : tile);
+        const int slot_tile = 2 * pt + static_cast<int>(rank);          // position in the (compacted) tile list
+        const bool ghost = slot_tile >= n_tiles;
+        const int list_pos = ghost ? n_tiles - 1 : slot_tile;
+        const int tile = p.active_tiles ? p.active_tiles[list_pos] : list_pos;
+        const TileInfo ti = cur.at(p.L, tile);
         const int t = ti.t0 + dt, u = ti.u0 + du;
         const bool valid = !ghost && (t < ti.T) && (u <= ti.U);
         const size_t grow = static_cast<size_t>(tile) * kBM + r;
@@ -1093,15 +1098,15 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P, ++it) {
         const int slot = it % p.NS, use = it / p.NS;
         const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
-        const int tile = 2 * pt + static_cast<int>(rank);
+        const int slot_tile = 2 * pt + static_cast<int>(rank);
         if (use > 0) {
           mbar_wait(&hfree_bar[slot], (use - 1) & 1);                     // local dh pass done with the slot
           if (ht == 0) wait_counter_ge(p.done + pair * p.NS + slot, static_cast<unsigned>(p.n_out * use));
           named_bar_sync(2, kHgenThreads);                                 // consumers done with the slot
         }
         TileInfo ti;
-        if (tile < p.n_tiles_total) {
-          ti = cur.at(p.L, tile);
+        if (slot_tile < n_tiles) {
+          ti = cur.at(p.L, p.active_tiles ? p.active_tiles[slot_tile] : slot_tile);
         } else {
           ti.b = 0; ti.t0 = 0; ti.u0 = 0; ti.T = 0; ti.U = -1;             // ghost half: all-zero rows
         }

@@ -361,3 +361,41 @@ def test_two_live_graphs_share_one_scratch_workspace():
         ref = O.rnnt_joint_loss(f.numpy(), g.numpy(), W.numpy(), bias.numpy(), y.numpy(), fl, yl, 28, faithful=True)
         for k, t in (("df", fd), ("dg", gd), ("dW", Wd), ("db", bd)):
             assert rel(t.grad.cpu().numpy(), ref[k]) < TOL, k
+
+
+def test_backward_walks_only_tiles_with_occupancy_and_loses_nothing(kernel_path):
+    """The backward mega-kernel walks the compacted list of lattice tiles whose cells have non-zero arc occupancy; a tile
+    whose occupancies all underflow to zero contributes exact zeros to every gradient.  Same gradients with the list and
+    with every tile (up to the order of the fp32 atomics), fewer tiles walked, and an utterance whose upstream gradient
+    is zero costs no tiles at all."""
+    import ctypes
+    from myrtlespeech_b200 import _lib, functional as F
+    if kernel_path != "persistent":
+        pytest.skip("the tile list belongs to the persistent backward kernel")
+    lib = _lib.load()
+    B, T, U, V, H = 3, 300, 60, 64, 64
+    f, g, W, bias, y, fl, yl = make(41, B, T, U, V, H, V - 1, False)
+    gl = [1.0, 0.0, 0.5]
+    out = {}
+    counts = {}
+    for mode in (0, -1):
+        lib.rnnt_debug_set(b"prune", mode)
+        try:
+            out[mode] = run_cuda(f, g, W, bias, y, fl, yl, V - 1, grad_loss=gl)
+            ws = next(iter(F._ws_pool.values()))
+            n = (ctypes.c_int * 2)()
+            if mode == 0:
+                _lib.check(lib.rnnt_debug_read_active_tiles(ws.data_ptr(), B, T, U, V, H, n))
+                counts = dict(active=n[0], total=n[1])
+        finally:
+            lib.rnnt_debug_set(b"prune", 0)
+    per_utt = ((T + 15) // 16) * ((U + 1 + 7) // 8)
+    assert counts["total"] == B * per_utt
+    assert 0 < counts["active"] < 2 * per_utt, counts          # utterance 1 (grad 0) costs nothing; the others lose their corners
+    for k in ("df", "dg", "dW", "db"):
+        assert rel(out[0][k], out[-1][k]) < 1e-6, k
+    assert np.all(out[0]["df"][1] == 0) and np.all(out[0]["dg"][1] == 0)
+    ref = O.rnnt_joint_loss(f.numpy(), g.numpy(), W.numpy(), bias.numpy(), y.numpy(), fl, yl, V - 1, grad_loss=np.array(gl),
+                            faithful=True)
+    for k in ("df", "dg", "dW", "db"):
+        assert rel(out[0][k], ref[k]) < TOL, k
