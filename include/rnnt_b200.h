@@ -81,6 +81,28 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
                         int V, int H, int blank, const float* grad_loss, float* df, float* dg, float* dW,
                         float* db, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same pair with the joint's activations KEPT between the calls.  rnnt_fused_forward above never writes the
+ * B*T*(U+1)*V logits and rnnt_fused_backward recomputes h = tanh(f + g) and the logits (2 of the 8 N*H*V flops of a step
+ * and N*H tanh); with 180 GB of HBM per GPU the other trade is usually the better one: the forward call also writes the
+ * logits (fp16, base-2, bias included) and h (bf16) of every lattice row into `kept`, a device buffer of
+ * rnnt_fused_kept_bytes(...) bytes owned by the caller (6.8 GB at B=32 T=500 U=100 V=H=1024), and the backward call
+ * streams them back instead of running the recompute GEMM.  The buffer must stay untouched between the two calls; it is
+ * the only state outside `workspace` (several live forward passes need one buffer each).  rnnt_fused_kept_bytes returns 0
+ * where nothing can be kept (more than 4096 vocabulary columns); a NULL / too small buffer, or a shape the one-launch
+ * backward kernel does not cover, silently selects the recompute schedule.  Gradients differ from the recompute schedule
+ * only through the fp16 rounding of the kept logits (relative 2^-11 on a logit, below the bf16 rounding of dz that both
+ * schedules share); the blank and label columns use the exact fp32 log-probabilities in both. */
+size_t rnnt_fused_kept_bytes(int B, int Tmax, int Umax, int V, int H);
+int rnnt_fused_forward_keep(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+                            const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax,
+                            int V, int H, int blank, float* loss, void* workspace, size_t workspace_bytes,
+                            void* kept, size_t kept_bytes, void* stream);
+int rnnt_fused_backward_kept(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+                             const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax,
+                             int V, int H, int blank, const float* grad_loss, float* df, float* dg, float* dW,
+                             float* db, void* workspace, size_t workspace_bytes, const void* kept,
+                             size_t kept_bytes, void* stream);
+
 /* Loss on materialised log-probabilities: lp_blank, lp_label f32 [B][Tmax][Umax+1] (natural layout,
  * lp_label[b][t][u] = log p(y[b][u] | t,u), column Umax unused).  Writes loss[B] and the arc
  * occupancies c_blank, c_label f32 [B][Tmax][Umax+1] with
@@ -162,7 +184,8 @@ void rnnt_debug_set(const char* key, int value);          /* "slab_tiles", "time
                                                               "path" (1 persistent kernels, 0 per-slab kernels),
                                                               "ring_slots" (2..4), "gemm_dbg" (bring-up switches),
                                                               "prune" (-1: the backward pass walks every tile; default 0: only
-                                                              tiles with non-zero occupancy), "prune_log2_eps" (threshold 2^v) */
+                                                              tiles with non-zero occupancy), "prune_log2_eps" (threshold 2^v),
+                                                              "keep" (0: *_keep / *_kept ignore their buffer) */
 long long rnnt_debug_get(const char* key);                /* "launches": kernels launched since the last reset */
 /* In "time_kernels" mode every kernel launch is bracketed by CUDA events on its stream; this call
  * synchronises, sums the durations per kernel class (hgen, joint_fwd, joint_dz, joint_dh, joint_dw,

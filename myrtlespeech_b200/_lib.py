@@ -23,6 +23,9 @@ SIGNATURES = {
     "rnnt_fused_state_bytes": (_c_size_t, [_c_int] * 5),
     "rnnt_fused_forward": (_c_int, [_vp] * 7 + [_c_int] * 6 + [_vp, _vp, _c_size_t, _vp]),
     "rnnt_fused_backward": (_c_int, [_vp] * 7 + [_c_int] * 6 + [_vp] * 5 + [_vp, _c_size_t, _vp]),
+    "rnnt_fused_kept_bytes": (_c_size_t, [_c_int] * 5),
+    "rnnt_fused_forward_keep": (_c_int, [_vp] * 7 + [_c_int] * 6 + [_vp, _vp, _c_size_t, _vp, _c_size_t, _vp]),
+    "rnnt_fused_backward_kept": (_c_int, [_vp] * 7 + [_c_int] * 6 + [_vp] * 5 + [_vp, _c_size_t, _vp, _c_size_t, _vp]),
     "rnnt_lattice_workspace_bytes": (_c_size_t, [_c_int] * 3),
     "rnnt_lattice_forward": (_c_int, [_vp] * 4 + [_c_int] * 3 + [_vp] * 3 + [_vp, _c_size_t, _vp]),
     "rnnt_greedy_joint_argmax": (_c_int, [_vp] * 6 + [_c_int] * 4 + [_vp]),

@@ -26,9 +26,11 @@ thread_local char g_err[512] = "";
 int g_slab_tiles_override = 0;
 int g_path = 1;  // 1 = persistent kernels (persist.cu), 0 = per-slab kernels (joint.cu)
 int g_ring_slots = 2;
+int g_kgk_override = 0;  // the same for the kept-logits schedule
 int g_kg_override = 0;   // bring-up: K-groups of dW consumers in the backward mega-kernel (0 = plan's choice)
 int g_cluster = 2;      // forward kernel: CTAs per cluster; 4 = two CTA pairs sharing W through TMA multicast
                         // (measured slower: only 132 of the 148 SMs can host 4-clusters)
+int g_keep = 1;      // 0: a buffer passed to the *_keep / *_kept calls is ignored (recompute schedule)
 int g_prune = 0;            // backward mega-kernel: >= 0 walks only tiles that carry occupancy; -1 = every tile
 int g_prune_log2_eps = -100000;  // occupancy threshold 2^v (default: exact zero only)
 int g_fwd_hgen_warps = 0;  // 0 = by shape; 4 / 8 force the forward kernel's number of hgen warps
@@ -95,7 +97,8 @@ struct Plan {
   int max_tiles, slab_tiles;
   size_t o_prefix, o_flens, o_ylens, o_lse, o_lpb, o_lpl, o_alpha, o_beta, o_c1, o_c2, o_lnpb, o_lnp64, o_wt, o_h, o_dz, o_hs, o_hring, o_dzring, o_flags, o_tflags, o_active, o_nactive;
   int mega_ok, n_vt, n_ht, n_out, KG, C, P, NS;
-  size_t state_bytes, total;
+  int keep_ok, KGk, Ck, Pk;      // role split of the mega-kernel when the forward pass kept the logits (no recompute GEMM)
+  size_t state_bytes, total, kept_bytes, o_keep_h;
 };
 
 Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
@@ -147,13 +150,26 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
     for (int hb = 0; hb < p.n_ht; ++hb) cons += p.n_vt * 4 * ((H - hb * 512 > 256) ? 8 : 4) * 128.0;
     const double c_ideal = (kMaxPersistCtas / 2) * cons / (cons + prod);
     p.KG = static_cast<int>(c_ideal / p.n_out + 0.5);
+    // kept logits: the producers run the dh pass only (dz is a streaming pass of the front-end warps)
+    const double mma_k = ch_h * kb_v * 4 * 128, epi_k = 10500.0 * H / 256;
+    const double prod_k = mma_k > epi_k ? mma_k : epi_k;
+    p.KGk = static_cast<int>((kMaxPersistCtas / 2) * cons / (cons + prod_k) / p.n_out + 0.5);
   }
   if (g_kg_override > 0) p.KG = g_kg_override;
+  if (g_kgk_override > 0) p.KGk = g_kgk_override;
   if (p.KG < 1) p.KG = 1;
+  if (p.KGk < 1) p.KGk = 1;
   p.C = p.n_out * p.KG;
   p.P = kMaxPersistCtas / 2 - p.C;
+  p.Ck = p.n_out * p.KGk;
+  p.Pk = kMaxPersistCtas / 2 - p.Ck;
+  if (p.Pk > p.P) { p.Pk = p.P; p.KGk = p.KG; p.Ck = p.C; }   // the rings are sized for P producer pairs
   p.NS = g_ring_slots;
   p.mega_ok = p.C <= 40 && p.P >= 1 && p.Vp <= 4096;   // 16 V chunks / 4096 bias columns in the mega-kernel
+  p.keep_ok = p.mega_ok && p.Ck <= 40 && p.Pk >= 1;
+  // fp16 base-2 logits and bf16 h of every lattice row, kept from the forward to the backward pass in a buffer of the caller
+  p.o_keep_h = align_up(2 * static_cast<size_t>(p.max_tiles) * kTileRows * p.Vp, 1024);
+  p.kept_bytes = p.Vp <= 4096 ? p.o_keep_h + 2 * static_cast<size_t>(p.max_tiles) * kTileRows * H : 0;
   p.o_tflags = take(sizeof(int) * static_cast<size_t>(p.max_tiles));   // backward-pass tile list (lattice.cu)
   p.o_active = take(sizeof(int) * static_cast<size_t>(p.max_tiles));
   p.o_nactive = take(sizeof(int) * 4);
@@ -212,6 +228,24 @@ int make_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uin
   if (r != CUDA_SUCCESS)
     return fail(RNNT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu pitch=%llu box=%ux%u", (int)r,
                 (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch, box_cols, box_rows);
+  return RNNT_OK;
+}
+
+// fp16 [rows][cols] map for the kept logits: 32 x 32 boxes (64-byte rows), 64-byte swizzle
+// (forward pass, stores), or 64 x 128 boxes with the 128-byte swizzle (backward pass, loads)
+int make_map_f16(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch, bool load_boxes) {
+  auto enc = get_encode();
+  if (!enc) return fail(RNNT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch * 2};
+  cuuint32_t box[2] = {load_boxes ? 64u : 32u, load_boxes ? 128u : 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, load_boxes ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(RNNT_ERR_CUDA, "cuTensorMapEncodeTiled (kept logits) failed (%d) cols=%llu rows=%llu", (int)r,
+                (unsigned long long)cols, (unsigned long long)rows);
   return RNNT_OK;
 }
 
@@ -366,7 +400,7 @@ int g_decode_res = 1;    // keep the projection weights resident in TMEM when th
 
 extern "C" {
 
-int rnnt_abi_version(void) { return 2; }
+int rnnt_abi_version(void) { return 3; }
 
 const char* rnnt_last_error(void) { return g_err; }
 
@@ -380,6 +414,7 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "decode_resident")) g_decode_res = value;
   if (!strcmp(key, "decode_l_late")) g_decode_l_late = value;
   if (!strcmp(key, "mega_kg")) g_kg_override = value;
+  if (!strcmp(key, "mega_kg_kept")) g_kgk_override = value;
   if (!strcmp(key, "decode_variant") && (value == 0 || value == 1)) g_decode_variant = value;
   if (!strcmp(key, "decode_cluster") && value >= 1 && value <= 16) g_decode_cluster = value;
   if (!strcmp(key, "mega_cooperative")) set_bwd_mega_cooperative(value);  // 0: plain launch (ncu cannot replay cooperative launches)
@@ -387,6 +422,7 @@ void rnnt_debug_set(const char* key, int value) {
   if (!strcmp(key, "cluster_bwd") && (value == 2 || value == 4)) g_cluster_bwd = value;
   if (!strcmp(key, "fwd_hgen_warps")) g_fwd_hgen_warps = value;
   if (!strcmp(key, "prune")) g_prune = value;
+  if (!strcmp(key, "keep")) g_keep = value;
   if (!strcmp(key, "prune_log2_eps")) g_prune_log2_eps = value;
   if (!strcmp(key, "ring_slots") && value >= 2 && value <= 4) g_ring_slots = value;
   if (!strcmp(key, "reset_launches")) for (int i = 0; i < K_NCLASS; ++i) g_launches[i] = 0;
@@ -452,9 +488,20 @@ size_t rnnt_fused_state_bytes(int B, int Tmax, int Umax, int V, int H) {
   return make_plan(B, Tmax, Umax, V, H).state_bytes;
 }
 
-int rnnt_fused_forward(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+size_t rnnt_fused_kept_bytes(int B, int Tmax, int Umax, int V, int H) {
+  if (check_dims(B, Tmax, Umax, V, H) != RNNT_OK) return 0;
+  return make_plan(B, Tmax, Umax, V, H).kept_bytes;
+}
+
+// Whether a pair of calls with a `kept` buffer really keeps the activations: both calls evaluate this the same way.
+static bool keeps_activations(const Plan& p, const void* kept, size_t kept_bytes) {
+  return kept && p.kept_bytes > 0 && kept_bytes >= p.kept_bytes && g_path == 1 && p.keep_ok && g_keep != 0;
+}
+
+static int fused_forward_impl(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
                        const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax, int V,
-                       int H, int blank, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+                       int H, int blank, float* loss, void* workspace, size_t workspace_bytes, void* kept,
+                       size_t kept_bytes, void* stream) {
   int rc = check_dims(B, Tmax, Umax, V, H);
   if (rc) return rc;
   if (!f || !g || !W || !loss || !workspace || (Umax > 0 && !y)) return fail(RNNT_ERR_INVALID_ARGUMENT, "NULL pointer argument");
@@ -497,13 +544,24 @@ int rnnt_fused_forward(const void* f, const void* g, const void* W, const float*
       rc = make_map(&tm_w, W, H, V, H, 64, nc / 4);
       if (rc) return rc;
     }
+    CUtensorMap tm_z = tm_hs;   // placeholder when nothing is kept (never dereferenced)
+    const bool keep = keeps_activations(p, kept, kept_bytes);
     FwdPArgs pa{};
+    if (keep) {
+      uint8_t* kb = static_cast<uint8_t*>(kept);
+      const uint64_t keep_rows = static_cast<uint64_t>(p.max_tiles) * kTileRows;
+      if ((rc = make_map_f16(&tm_z, kb, p.Vp, keep_rows, p.Vp, false))) return rc;
+      // the h tiles go straight to their place in the kept buffer and are read back from there as the A operand
+      pa.hkeep = reinterpret_cast<__nv_bfloat16*>(kb + p.o_keep_h);
+      if ((rc = make_map(&tm_hs, pa.hkeep, H, keep_rows, H, 64, 128))) return rc;
+    }
+    pa.keep_z = keep ? 1 : 0;
     pa.L = L; pa.dbg = get_gemm_dbg(); pa.csize = csize; pa.hgen_warps = hgen_warps; pa.n_tiles_total = n_tiles; pa.V = V; pa.H = H; pa.nc = nc; pa.n_chunks = (V + nc - 1) / nc;
     pa.k_blocks = (H + 63) / 64; pa.blank = blank; pa.Umax = d.Umax;
     pa.f = static_cast<const __nv_bfloat16*>(f); pa.g = static_cast<const __nv_bfloat16*>(g);
     pa.hscratch = w.at<__nv_bfloat16>(p.o_hs);
     pa.bias = bias; pa.y = y; pa.lse_tile = w.at<float>(p.o_lse); pa.lpb = w.at<float>(p.o_lpb); pa.lpl = w.at<float>(p.o_lpl);
-    KLAUNCH(K_FWD, s, launch_fwd_persist(tm_hs, tm_w, pa, n_ctas, s));
+    KLAUNCH(K_FWD, s, launch_fwd_persist(tm_hs, tm_w, tm_z, pa, n_ctas, s));
   }
   FwdArgs a{bias, y, w.at<float>(p.o_lse), w.at<float>(p.o_lpb), w.at<float>(p.o_lpl)};
   for (int t0 = 0; g_path != 1 && t0 < n_tiles; t0 += p.slab_tiles) {
@@ -522,10 +580,25 @@ int rnnt_fused_forward(const void* f, const void* g, const void* W, const float*
   return RNNT_OK;
 }
 
-int rnnt_fused_backward(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+int rnnt_fused_forward(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+                       const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax, int V,
+                       int H, int blank, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  return fused_forward_impl(f, g, W, bias, y, f_lens_host, y_lens_host, B, Tmax, Umax, V, H, blank, loss, workspace,
+                            workspace_bytes, nullptr, 0, stream);
+}
+
+int rnnt_fused_forward_keep(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+                            const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax, int V,
+                            int H, int blank, float* loss, void* workspace, size_t workspace_bytes, void* kept,
+                            size_t kept_bytes, void* stream) {
+  return fused_forward_impl(f, g, W, bias, y, f_lens_host, y_lens_host, B, Tmax, Umax, V, H, blank, loss, workspace,
+                            workspace_bytes, kept, kept_bytes, stream);
+}
+
+static int fused_backward_impl(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
                         const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax, int V,
                         int H, int blank, const float* grad_loss, float* df, float* dg, float* dW, float* db,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+                        void* workspace, size_t workspace_bytes, const void* kept, size_t kept_bytes, void* stream) {
   int rc = check_dims(B, Tmax, Umax, V, H);
   if (rc) return rc;
   if (!f || !g || !W || !grad_loss || !df || !dg || !dW || !db || !workspace || (Umax > 0 && !y))
@@ -549,13 +622,15 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
   KLAUNCH(K_MISC, s, launch_transpose_w(static_cast<const __nv_bfloat16*>(W), w.at<__nv_bfloat16>(p.o_wt), V, H, p.Vp, s));
 
   const int nc_v = chunk_cols(V), nc_h = chunk_cols(H);
+  const bool keep = keeps_activations(p, kept, kept_bytes);
+  const int n_cons = keep ? p.Ck : p.C, n_kg = keep ? p.KGk : p.KG;
   if (g_path == 1 && p.mega_ok && max_ctas_bwd_mega(2) >= 2 * (p.P + p.C)) {
     // 4-clusters (operand multicast between two pairs of one role): both roles must start on a cluster boundary,
     // both W chunk widths must split into quarters, and only the co-resident capacity for 4-clusters (132 of 148
     // CTAs on this part) can be used, so the producers give up the difference.
-    int P = p.P;
+    int P = keep ? p.Pk : p.P;
     int csize = 2;
-    if (g_cluster_bwd == 4 && p.C % 2 == 0 && nc_v % 32 == 0 && nc_h % 32 == 0) {
+    if (!keep && g_cluster_bwd == 4 && p.C % 2 == 0 && nc_v % 32 == 0 && nc_h % 32 == 0) {
       int P4 = max_ctas_bwd_mega(4) / 2 - p.C;
       if (P4 > p.P) P4 = p.P;
       P4 &= ~1;
@@ -585,14 +660,24 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
     a.nc_v = nc_v; a.n_chunks_v = (V + nc_v - 1) / nc_v; a.kb_h = (H + 63) / 64;
     a.nc_h = nc_h; a.n_chunks_h = (H + nc_h - 1) / nc_h; a.kb_v = p.Vp / 64;
     a.blank = blank; a.Umax = d.Umax;
-    a.P = P; a.C = p.C; a.KG = p.KG; a.NS = p.NS; a.n_vt = p.n_vt; a.n_ht = p.n_ht; a.n_out = p.n_out;
+    a.P = P; a.C = n_cons; a.KG = n_kg; a.NS = p.NS; a.n_vt = p.n_vt; a.n_ht = p.n_ht; a.n_out = p.n_out;
     a.f = static_cast<const __nv_bfloat16*>(f); a.g = static_cast<const __nv_bfloat16*>(g);
-    a.h_ring = w.at<__nv_bfloat16>(p.o_hring);
+    a.h_ring = w.at<__nv_bfloat16>(p.o_hring); a.dz_ring = w.at<__nv_bfloat16>(p.o_dzring);
+    CUtensorMap tm_zl = tm_dz;   // placeholder when the logits are recomputed (never dereferenced)
+    if (keep) {
+      const uint8_t* kb = static_cast<const uint8_t*>(kept);
+      const uint64_t keep_rows = static_cast<uint64_t>(p.max_tiles) * kTileRows;
+      a.zlog = reinterpret_cast<const uint16_t*>(kb);
+      a.hkeep = reinterpret_cast<const __nv_bfloat16*>(kb + p.o_keep_h);
+      a.zcols = a.n_chunks_v * nc_v < p.Vp ? a.n_chunks_v * nc_v : p.Vp;
+      if ((rc = make_map_f16(&tm_zl, kb, p.Vp, keep_rows, p.Vp, true))) return rc;
+      if ((rc = make_map(&tm_h_mn, a.hkeep, H, keep_rows, H, 64, 64))) return rc;   // the consumers read h where the forward pass left it
+    }
     a.bias = bias; a.y = y; a.lse_tile = w.at<float>(p.o_lse); a.lpb = w.at<float>(p.o_lpb); a.lpl = w.at<float>(p.o_lpl);
     a.c1 = w.at<float>(p.o_c1); a.c2 = w.at<float>(p.o_c2); a.grad_loss = grad_loss;
     a.db = db; a.df = df; a.dg = dg; a.dW = dW;
     a.ready = w.at<unsigned>(p.o_flags); a.done = w.at<unsigned>(p.o_flags) + n_flags;
-    KLAUNCH(K_BWD_MEGA, s, launch_bwd_mega(tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a, 2 * (P + p.C), s));
+    KLAUNCH(K_BWD_MEGA, s, launch_bwd_mega(tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, tm_zl, a, 2 * (P + n_cons), s));
     CUDA_TRY(cudaGetLastError());
     return RNNT_OK;
   }
@@ -619,6 +704,23 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
   }
   CUDA_TRY(cudaGetLastError());
   return RNNT_OK;
+}
+
+int rnnt_fused_backward(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+                        const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax, int V,
+                        int H, int blank, const float* grad_loss, float* df, float* dg, float* dW, float* db,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  return fused_backward_impl(f, g, W, bias, y, f_lens_host, y_lens_host, B, Tmax, Umax, V, H, blank, grad_loss, df, dg, dW,
+                             db, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+int rnnt_fused_backward_kept(const void* f, const void* g, const void* W, const float* bias, const int32_t* y,
+                             const int32_t* f_lens_host, const int32_t* y_lens_host, int B, int Tmax, int Umax, int V,
+                             int H, int blank, const float* grad_loss, float* df, float* dg, float* dW, float* db,
+                             void* workspace, size_t workspace_bytes, const void* kept, size_t kept_bytes,
+                             void* stream) {
+  return fused_backward_impl(f, g, W, bias, y, f_lens_host, y_lens_host, B, Tmax, Umax, V, H, blank, grad_loss, df, dg, dW,
+                             db, workspace, workspace_bytes, kept, kept_bytes, stream);
 }
 
 size_t rnnt_lattice_workspace_bytes(int B, int Tmax, int Umax) {

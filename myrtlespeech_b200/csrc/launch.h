@@ -108,6 +108,9 @@ struct FwdPArgs {
   int dbg;
   int csize;                  // CTAs per cluster: 2 (one CTA pair) or 4 (two pairs, W multicast)
   int hgen_warps;             // 4, or 8 for narrow vocabularies (the pass is bound by the tanh evaluations)
+  int keep_z;                 // != 0: the base-2 logits are also stored as fp16 through the tm_z map (<= 4096 columns)
+  __nv_bfloat16* hkeep;       // keep_z: [tiles][128][H] h tiles are written here (and read back as the A operand through
+                              // tm_hscratch, which then maps this buffer) instead of the per-CTA scratch
   int n_tiles_total;
   int V, H;
   int nc, n_chunks, k_blocks;
@@ -122,8 +125,8 @@ struct FwdPArgs {
   float* lpl;
 };
 // One persistent launch for the whole batch: hgen + logits (tcgen05) + online log-softmax.
-void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
-                        cudaStream_t s);
+void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const CUtensorMap& tm_z, const FwdPArgs& a,
+                        int n_ctas, cudaStream_t s);
 int smem_bytes_fwd_persist();
 int max_ctas_fwd_persist(int csize, int hgen_warps = 4);
 int read_persist_prof(unsigned long long* out, int n);
@@ -147,6 +150,7 @@ struct BwdPArgs {
   const __nv_bfloat16* f;
   const __nv_bfloat16* g;
   __nv_bfloat16* h_ring;       // [P][NS][256][H]
+  __nv_bfloat16* dz_ring;      // [P][NS][256][Vp]
   const float* bias;
   const int* y;
   const float* lse_tile;
@@ -159,13 +163,16 @@ struct BwdPArgs {
   float* df;
   float* dg;
   float* dW;
-  unsigned* ready;             // [P][NS] += 1 per producer epilogue warp (2 CTAs x 8) per use
+  const uint16_t* zlog;        // fp16 base-2 logits [tiles][128][Vp] kept by the forward pass, or null (recompute them)
+  const __nv_bfloat16* hkeep;  // with zlog: h [tiles][128][H] kept by the forward pass (tm_h_mn maps it; no hgen, no h ring)
+  int zcols;                   // columns of a zlog row the forward pass wrote (multiple of 32, <= Vp)
+  unsigned* ready;             // [P][NS] per use: += 1 per producer epilogue warp (2 CTAs x 8), or per CTA (2) with zlog
   unsigned* done;              // [P][NS] += 1 per consumer pair per use
 };
 // One persistent launch for the whole backward pass (see persist.cu).
 void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUtensorMap& tm_dz, const CUtensorMap& tm_wt,
                      const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, const CUtensorMap& tm_dz_st,
-                     const BwdPArgs& a, int n_ctas, cudaStream_t s);
+                     const CUtensorMap& tm_zl, const BwdPArgs& a, int n_ctas, cudaStream_t s);
 int smem_bytes_bwd_mega();
 int max_ctas_bwd_mega(int csize);
 int bwd_mega_cooperative();   // 1 while the cooperative (co-scheduled) launch is in use

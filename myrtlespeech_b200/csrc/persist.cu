@@ -46,7 +46,8 @@ constexpr int kMegaTmaWarp = 12, kMegaMmaWarp = 13;
 //   [6] hgen busy cycles  [7] epilogue busy cycles (between tfull and tempty arrive)
 __device__ unsigned long long g_pprof[160 * 8];
 __device__ unsigned long long g_pprof2[160 * 8];   // second bank (RNNT_PROFILE builds): per-pass chunk issue cycles
-__device__ unsigned long long g_pprof3[160 * 8];   // third bank (RNNT_PROFILE builds): dh-epilogue phase cycles of warp 0, summed
+__device__ unsigned long long g_pprof3[160 * 8];
+__device__ unsigned long long g_pprof4[160 * 8];   // fourth bank (RNNT_PROFILE builds): kept-logits dz pass, phase cycles of thread 0   // third bank (RNNT_PROFILE builds): dh-epilogue phase cycles of warp 0, summed
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -139,6 +140,13 @@ __device__ __forceinline__ void tma_load_2d_pair_mcast(uint32_t smem_dst, const 
 }
 // generic-proxy global writes -> visible to later async-proxy (TMA) reads
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// two fp32 -> one fp16x2 word (round to nearest even; `lo` in bits 0..15)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // h rows of one tile -> dst[128][H] (row = dt * 8 + du); rows outside the utterance's lattice are zero.
 // Called by the 128 hgen threads (ht = 0..127).  A thread owns one 8-column vector and a range of frames: with
@@ -253,7 +261,8 @@ constexpr int kFwdSmem = kFwdStages * kStageBytes + kMaxBiasCols * 4 + 1024 + 25
 // forward pass is bound by the tanh pass: two warps per scheduler overlap each other's MUFU latency and stores).
 template <int kHW>
 __global__ void __launch_bounds__((6 + kHW) * 32, 1)
-fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const FwdPArgs p) {
+fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const __grid_constant__ CUtensorMap tm_z, const FwdPArgs p) {
   constexpr int kStages = kFwdStages;
   constexpr int kFwdTmaWarp = 4 + kHW, kFwdMmaWarp = 5 + kHW;
   constexpr int kHT = kHW * 32;
@@ -290,6 +299,7 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_a);
     prefetch_tmap(&tm_b);
+    if (p.keep_z) prefetch_tmap(&tm_z);
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], quad ? 2 : 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8);
@@ -333,7 +343,9 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             } else if (elect_one()) {
               if (leader) { if (tx) mbar_arrive_expect_tx(&full_bar[s], 2 * tx); else mbar_arrive(&full_bar[s]); }
               const uint32_t sa = sbase + s * kStageBytes;
-              if (!(p.dbg & 8)) tma_load_2d_pair_a(sa, &tm_a, &full_bar[s], k * kBK, a_row0 + hb * kBM);
+              if (!(p.dbg & 8))
+                tma_load_2d_pair_a(sa, &tm_a, &full_bar[s], k * kBK,
+                                   p.keep_z ? (2 * pt + static_cast<int>(rank)) * kBM : a_row0 + hb * kBM);
               if (!(p.dbg & 16)) {
                 if (quad)   // this CTA fetches one quarter of the chunk and multicasts it to its twin in the other pair
                   tma_load_2d_pair_mcast(sa + kAStage + cpair * (b_bytes >> 1), &tm_b, &full_bar[s], k * kBK,
@@ -395,6 +407,13 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     for (int c = et; c < ncols; c += kEpiThreads)
       sbias[c] = (c < p.V) ? (p.bias ? p.bias[c] * kLog2e : 0.0f) : -INFINITY;
     named_bar_sync(1, kEpiThreads);
+    // keep_z: the base-2 logits (bias included) also go to HBM as fp16 for the backward pass.  Each warp stages 32 rows x
+    // 32 columns (64-byte rows, TMA 64-byte swizzle: conflict-free 16-byte stores) in one of its two 2 KB slices -- they
+    // live in the upper half of the bias table, which a kept vocabulary (<= 4096 columns) does not use -- and lane 0
+    // TMA-stores the slice.
+    uint8_t* zsl = reinterpret_cast<uint8_t*>(sbias) + (kMaxBiasCols / 2) * 4 + warp * 4096;
+    const uint32_t zrow = smem_u32(zsl) + lane * 64;
+    const int zsw = (lane >> 1) & 3;
 
     int gc = 0;
     long long busy = 0;
@@ -440,6 +459,21 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           mx = mn;
           if (static_cast<unsigned>(p.blank - c0) < 32u) zb = pick32(v, p.blank - c0);
           if (static_cast<unsigned>(label - c0) < 32u) zl = pick32(v, label - c0);
+          if (p.keep_z) {
+            const uint32_t zo = (g & 1) * 2048;
+            if (lane == 0) tma_store_wait_read1();   // the store that last used this slice has read it
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              sts128(zrow + zo + ((q ^ zsw) << 4), pack_f16x2(v[8 * q + 0], v[8 * q + 1]), pack_f16x2(v[8 * q + 2], v[8 * q + 3]),
+                     pack_f16x2(v[8 * q + 4], v[8 * q + 5]), pack_f16x2(v[8 * q + 6], v[8 * q + 7]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (!ghost) tma_store_2d(&tm_z, zsl + zo, c0, tile * kBM + lq * 32);
+              tma_store_commit();
+            }
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -453,6 +487,7 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         p.lpl[didx] = (u < ti.U) ? (zl - lse2) * kLn2 : kNeg;
       }
     }
+    if (p.keep_z && lane == 0) tma_store_wait_all0();
     if ((p.dbg & 4) && et == 0) g_pprof[blockIdx.x * 8 + 7] = busy;
   } else {
     // ------------------------------- hgen -----------------------------------------
@@ -469,7 +504,9 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       PCNT_BEGIN(h);
       if (tile < p.n_tiles_total) {
         const TileInfo ti = cur.at(p.L, tile);
-        hgen_tile<kHT>(ti, p.f, p.g, my_scratch + static_cast<size_t>(hb) * kBM * p.H, p.H, p.L.Tmax, p.L.U1max, ht);
+        hgen_tile<kHT>(ti, p.f, p.g,
+                       p.keep_z ? p.hkeep + static_cast<size_t>(tile) * kBM * p.H : my_scratch + static_cast<size_t>(hb) * kBM * p.H,
+                       p.H, p.L.Tmax, p.L.U1max, ht);
       }
       __threadfence();
       fence_proxy_async_global();
@@ -545,7 +582,6 @@ __device__ __forceinline__ uint4 ld_ca_u4(const void* ptr) {
 }
 __device__ __forceinline__ void tma_store_wait_all1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 constexpr int kMegaThreads = 512;  // 16 warps, roles above (warps 8, 9 idle)
 
@@ -596,11 +632,114 @@ __device__ __forceinline__ void reduce_over_frames(const float (&v)[32], int lan
   }
 }
 
+// ---- dz of one tile from the logits the forward pass kept ------------------------------------------------------------
+// When the forward pass stored the base-2 logits z2 = log2(e) (W h + bias) as fp16, dz = c0 2^(z2 - lse2) - [blank] c1 -
+// [label] c2 is a streaming pass: no recompute GEMM, no TMEM round trip.  Three warp roles share a ring of three
+// 128-row x 64-column boxes (16 KB, 128-byte swizzle) in shared memory:
+//   * post warp 8 TMA-loads the tile's logits box by box (mbarrier completion -- register prefetch cannot cover the
+//     latency: a warp's loads share six scoreboards, so waiting for the oldest load waits for the youngest on the same
+//     counter: measured 700 cycles per row),
+//   * the 128 transform threads (warps 10, 11, 14, 15) each own one lattice row (row scalars in registers) and turn a box
+//     into bf16 dz IN PLACE (conflict-free 16-byte accesses under the swizzle); the two special columns take their exact
+//     fp32 values (lp_blank / lp_label), as in the recompute path,
+//   * post warps 8 and 9 TMA-store the box into the ring slot, add its column sums (db, from the staged bf16 values, as in
+//     the recompute path) and recycle the buffer.
+// The transform warps never touch the ring slot, so they run ahead of the slot's reuse by the depth of the box ring.
+constexpr int kZBoxBytes = kBM * 64 * 2;   // 16 KB
+constexpr int kZBoxes = 3;
+__device__ __forceinline__ void prefetch_l2_bulk(const void* ptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float2 f16x2_to_f32(uint32_t w) {
+  float2 r;
+  asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi; }" : "=f"(r.x), "=f"(r.y) : "r"(w));
+  return r;
+}
+// Offsets of the three boxes from the producer's union region: the two gaps next to the dh epilogue's dg partial sums and
+// the bias table (none of which the kept-logits schedule uses otherwise); all 1 KB aligned.
+__device__ __forceinline__ uint32_t zbox_offset(int b) { return b == 0 ? 16384u : (b == 1 ? 51200u : static_cast<uint32_t>(kUnionBytes)); }
+
+// One tile by the 128 transform threads; `q` counts boxes over the whole launch (ring position / phase).
+__device__ __forceinline__ void dz_transform_tile(const BwdPArgs& p, const TileInfo& ti, int tile, uint8_t* uni, uint64_t* zfull,
+                                                  uint64_t* zdone, int& q, int ht) {
+  const int lane = ht & 31;
+  const int dt = ht >> 3, du = ht & 7;
+  const int t = ti.t0 + dt, u = ti.u0 + du;
+  const bool valid = (t < ti.T) && (u <= ti.U);
+  float c1g = 0.0f, c2g = 0.0f, lse2 = 1.0e30f, lpb_r = 0.0f, lpl_r = 0.0f;
+  int label = -1;
+  if (valid) {
+    const size_t didx = diag_index(p.L, ti.b, t, u);
+    const float gl = p.grad_loss[ti.b];
+    c1g = p.c1[didx] * gl;
+    c2g = p.c2[didx] * gl;
+    lse2 = p.lse_tile[static_cast<size_t>(tile) * kBM + ht] * kLog2e;
+    lpb_r = p.lpb[didx];
+    if (u < ti.U) { lpl_r = p.lpl[didx]; label = p.y[static_cast<size_t>(ti.b) * p.Umax + u]; }
+  }
+  const float c0g = c1g + c2g;
+  const float dv_blank = c0g * ex2f(lpb_r * kLog2e) - c1g;
+  const float dv_label = c0g * ex2f(lpl_r * kLog2e) - c2g;
+  // c0 2^(z2 - lse2) = +-2^(z2 - koff): the row's scale rides in the exponent (one add and one ex2 per element)
+  const float koff = c0g != 0.0f ? lse2 - lg2f(fabsf(c0g)) : 1.0e30f;
+  const uint32_t sgn = c0g < 0.0f ? 0x80008000u : 0u;
+  const int nbox = p.Vp >> 6;
+  const int sw = ht & 7;
+  for (int k = 0; k < nbox; ++k, ++q) {
+    const int b = q % kZBoxes;
+    const uint32_t rowp = smem_u32(uni + zbox_offset(b)) + ht * 128;
+#ifdef RNNT_PROFILE
+    long long z_t = clock64();
+#define ZT(i) do { if (ht == 0) { const long long n_ = clock64(); g_pprof4[blockIdx.x * 8 + (i)] += n_ - z_t; z_t = n_; } } while (0)
+#else
+#define ZT(i) do { } while (0)
+#endif
+    mbar_wait(&zfull[b], (q / kZBoxes) & 1);
+    ZT(0);
+    // all eight loads first, then the arithmetic, then the stores: the shared-memory accesses are volatile asm and keep
+    // their order, so a load-compute-store loop serialises the eight chains (2.3 k instead of 1.7 k cycles per box)
+    uint32_t x[8][4];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(x[c][0]), "=r"(x[c][1]), "=r"(x[c][2]), "=r"(x[c][3]) : "r"(rowp + ((c ^ sw) << 4)));
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const bool have = k * 64 + c * 8 < p.zcols;   // columns the forward pass wrote
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = f16x2_to_f32(x[c][e]);
+        const uint32_t o = pack_bf16x2(ex2f(a.x - koff), ex2f(a.y - koff)) ^ sgn;
+        x[c][e] = have ? o : 0u;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sts128(rowp + ((c ^ sw) << 4), x[c][0], x[c][1], x[c][2], x[c][3]);
+    {
+      const int cb = p.blank - k * 64;
+      if (static_cast<unsigned>(cb) < 64u)
+        sts16(rowp + (((cb >> 3) ^ sw) << 4) + (cb & 7) * 2, __bfloat16_as_ushort(__float2bfloat16_rn(dv_blank)));
+      const int cl = label - k * 64;
+      if (label >= 0 && static_cast<unsigned>(cl) < 64u)
+        sts16(rowp + (((cl >> 3) ^ sw) << 4) + (cl & 7) * 2, __bfloat16_as_ushort(__float2bfloat16_rn(dv_label)));
+    }
+    ZT(1);
+    fence_proxy_async_smem();     // the post warp's TMA store reads these rows through the async proxy
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&zdone[b]);
+    ZT(2);
+  }
+#ifdef RNNT_PROFILE
+  if (ht == 0) g_pprof4[blockIdx.x * 8 + 7] += nbox;
+#endif
+}
+
 __global__ void __launch_bounds__(kMegaThreads, 1)
 bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_wt,
                 const __grid_constant__ CUtensorMap tm_dz_mn, const __grid_constant__ CUtensorMap tm_h_mn,
-                const __grid_constant__ CUtensorMap tm_dz_st, const BwdPArgs p) {
+                const __grid_constant__ CUtensorMap tm_dz_st, const __grid_constant__ CUtensorMap tm_zl, const BwdPArgs p) {
   constexpr int kStages = kBwdStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -614,6 +753,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   uint64_t* hfree_bar = bars + 16;                // [kMaxNS] epilogue (dh pass finished with the slot's h) -> hgen
   uint64_t* dzr_bar = bars + 20;                  // [kMaxVChunks] dz chunk stored and visible -> TMA (dh pass)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20 + kMaxVChunks);
+  uint64_t* zfull_bar = bars + 21 + kMaxVChunks;    // [kZBoxes] kept logits: post warp 8 (TMA load) -> transform warps
+  uint64_t* zdone_bar = bars + 24 + kMaxVChunks;    // [kZBoxes] transform warps (4) -> post warps: box holds dz
+  uint64_t* zempty_bar = bars + 27 + kMaxVChunks;   // [kZBoxes] post warp 9 -> post warp 8: box read, may be refilled
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -629,6 +771,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   const int n_tiles = p.active_tiles ? *p.n_active : p.n_tiles_total;
   const int n_ptiles = (n_tiles + 1) >> 1;
   const bool is_producer = pair < p.P;
+  const bool keep = p.zlog != nullptr;   // dz from the logits the forward pass kept (front-end warps) instead of a recompute GEMM
   const bool lockstep = p.csize == 4 && (is_producer || p.cons_share);   // this cluster's two pairs run in lockstep
   const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * cpair));
   const uint16_t all_mask = lockstep ? 0xF : pair_mask;
@@ -638,11 +781,16 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_h); prefetch_tmap(&tm_w); prefetch_tmap(&tm_dz);
     prefetch_tmap(&tm_wt); prefetch_tmap(&tm_dz_mn); prefetch_tmap(&tm_h_mn); prefetch_tmap(&tm_dz_st);
+    if (p.zlog) prefetch_tmap(&tm_zl);
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], lockstep ? 2 : 1); }
     // producers: 8 epilogue warps per CTA; consumers: 4 flush warps per CTA (periodic flush of the dW accumulators)
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], is_producer ? 16 : 8); }
-    for (int i = 0; i < kMaxNS; ++i) { mbar_init(&hfull_bar[i], kHgenThreads); mbar_init(&hfree_bar[i], 8); }
+    // kept logits: a slot is "full" when post warp 8 has stored its dz rows (its h is not in the ring at all)
+    for (int i = 0; i < kMaxNS; ++i) { mbar_init(&hfull_bar[i], p.zlog ? 1 : kHgenThreads); mbar_init(&hfree_bar[i], 8); }
     for (int i = 0; i < kMaxVChunks; ++i) mbar_init(&dzr_bar[i], 8);
+    for (int i = 0; i < kZBoxes; ++i) {
+      mbar_init(&zfull_bar[i], 1); mbar_init(&zdone_bar[i], kHgenThreads / 32); mbar_init(&zempty_bar[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == kMegaMmaWarp) {
@@ -677,7 +825,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           const int slot = it % p.NS, use = it / p.NS;
           const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
           { PCNT_BEGIN(a); mbar_wait(&hfull_bar[slot], use & 1); PCNT_END(a, w_hfull); }
-          for (int j = 0; j < p.n_chunks_v; ++j) {
+          for (int j = 0; j < (keep ? 0 : p.n_chunks_v); ++j) {   // kept logits: no recompute GEMM, dz is already in the slot
             for (int k = 0; k < p.kb_h; ++k) {
               { PCNT_BEGIN(a); mbar_wait(&empty_bar[s], ph ^ 1); PCNT_END(a, w_empty); }
               if ((p.dbg & 256) && n_issued >= kStages) {
@@ -703,7 +851,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           int dz_ready = -1;
           for (int j = 0; j < p.n_chunks_h; ++j) {
             for (int k = 0; k < p.kb_v; ++k) {
-              if (j == 0) {
+              if (j == 0 && !keep) {
                 int cj = (k * kBK + kBK - 1) / p.nc_v;
                 if (cj > p.n_chunks_v - 1) cj = p.n_chunks_v - 1;
                 while (dz_ready < cj) {
@@ -753,7 +901,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         const long long c_begin = clock64();
         const unsigned long long ns_begin = gtimer_ns();
         for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P) {
-          for (int pass = 0; pass < 2; ++pass) {
+          for (int pass = keep ? 1 : 0; pass < 2; ++pass) {
             const int n_chunks = pass == 0 ? p.n_chunks_v : p.n_chunks_h;
             const int k_blocks = pass == 0 ? p.kb_h : p.kb_v;
             const uint32_t idesc = pass == 0 ? idesc_v : idesc_h;
@@ -803,8 +951,10 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       uint8_t* set_base = uni + half * (kBM * kDhPitch * 4);   // this set's fp32 dh tile; its dz staging lives inside
       uint8_t* slice0 = set_base + wi * 8192;                  // this warp's two 32-row x 128-byte staging slices
       const int ncols_v = p.n_chunks_v * p.nc_v;
-      for (int c = half * kEpiThreads + et; c < ncols_v; c += 2 * kEpiThreads)
-        sbias[c] = (c < p.V) ? (p.bias ? p.bias[c] * kLog2e : 0.0f) : -INFINITY;
+      if (!keep) {
+        for (int c = half * kEpiThreads + et; c < ncols_v; c += 2 * kEpiThreads)
+          sbias[c] = (c < p.V) ? (p.bias ? p.bias[c] * kLog2e : 0.0f) : -INFINITY;
+      }
       named_bar_sync(4, 2 * kEpiThreads);
       // dz boxes (64 columns) of a chunk owned by this warp: 2*half + {0, 1}, as far as the chunk reaches
       int n_my_box = (p.nc_v + 63) / 64 - 2 * half;
@@ -832,7 +982,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         mbar_wait(&hfull_bar[slot], use & 1);  // acquire the hgen warps' writes of this slot's h
 
         // ---- dz pass: each warp stages and TMA-stores its own 32-row slices; no CTA-wide barrier ----
-        {
+        if (!keep) {
           float c1g = 0.0f, c2g = 0.0f, lse2 = 1.0e30f, lpb_r = 0.0f, lpl_r = 0.0f;
           if (valid) {
             const float gl = p.grad_loss[ti.b];
@@ -949,7 +1099,8 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         // ---- dh pass: set `half` owns the 32-column groups g = 4*half .. 4*half + 3 of every 256-column chunk ----
         {
           named_bar_sync(set_bar, kEpiThreads);  // every warp of the set is done with its dz staging (TMA reads finished)
-          const __nv_bfloat16* hrow = p.h_ring + (static_cast<size_t>(ring_row) + r) * p.H;
+          const __nv_bfloat16* hrow = keep ? p.hkeep + (static_cast<size_t>(tile) * kBM + r) * p.H
+                                           : p.h_ring + (static_cast<size_t>(ring_row) + r) * p.H;
           // partial dg sums of the set's four warps: [group 4][quad 4][label position 8][32 columns] fp32 = 16 KB, the
           // eight 16-byte chunks of a row XOR-swizzled with the label position (conflict-free 128-bit accesses)
           const uint32_t part_s = smem_u32(set_base);
@@ -1095,6 +1246,18 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       int it = 0;
       TileCursor cur;
       cur.init(p.L);
+      if (keep) {
+        // kept logits: these warps turn logit boxes into dz boxes (dz_transform_tile); h is not recomputed
+        int zq = 0;
+        for (int pt = pair; pt < n_ptiles; pt += p.P) {
+          const int slot_tile = 2 * pt + static_cast<int>(rank);
+          if (slot_tile >= n_tiles) continue;                              // empty half of an odd last pair-tile
+          const int tile = p.active_tiles ? p.active_tiles[slot_tile] : slot_tile;
+          // this tile's h rows are read by the dh epilogue a dz pass later: pull them into L2 now
+          prefetch_l2_bulk(p.hkeep + (static_cast<size_t>(tile) * kBM + ht) * p.H, static_cast<uint32_t>(p.H) * 2u);
+          dz_transform_tile(p, cur.at(p.L, tile), tile, uni, zfull_bar, zdone_bar, zq, ht);
+        }
+      } else {
       for (int pt = pair, pf = pt_first; pf < n_ptiles; pt += p.P, pf += p.P, ++it) {
         const int slot = it % p.NS, use = it / p.NS;
         const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
@@ -1116,6 +1279,96 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         __threadfence();
         fence_proxy_async_global();
         mbar_arrive(&hfull_bar[slot]);
+      }
+      }
+    } else if (keep) {
+      // ------------------------------- post warps 8, 9 (kept logits) --------------------
+      // Warp 8: loads the logit boxes, stores the dz boxes, owns the ring slot's hand-over (slot free -> slot full ->
+      // consumers); warps 8 and 9 add db from rows 0..63 / 64..127 of each box.
+      const bool main_warp = warp == 8;
+      const int nbox = p.Vp >> 6;
+      // loader cursor: the box that is loaded next (position in this CTA's tile sequence, box inside the tile)
+      int l_pt = pair, l_k = 0;
+      auto load_next = [&](int ql) {      // warp 8, converged: issue the load of box number ql into buffer ql % kZBoxes
+        while (l_pt < n_ptiles && 2 * l_pt + static_cast<int>(rank) >= n_tiles) l_pt += p.P;   // skip the empty half
+        if (l_pt >= n_ptiles) return;
+        if (elect_one()) {
+          const int pos = 2 * l_pt + static_cast<int>(rank);
+          const int tile = p.active_tiles ? p.active_tiles[pos] : pos;
+          const int b = ql % kZBoxes;
+          mbar_arrive_expect_tx(&zfull_bar[b], kZBoxBytes);
+          tma_load_2d(uni + zbox_offset(b), &tm_zl, &zfull_bar[b], l_k * 64, tile * kBM);
+        }
+        __syncwarp();
+        if (++l_k == nbox) { l_k = 0; l_pt += p.P; }
+      };
+      if (main_warp)
+        for (int i = 0; i < kZBoxes; ++i) load_next(i);
+      int q = 0, it = 0;
+      for (int pt = pair; pt < n_ptiles; pt += p.P, ++it) {
+        const int slot = it % p.NS, use = it / p.NS;
+        const int ring_row = ((pair * p.NS + slot) * 2 + static_cast<int>(rank)) * kBM;
+        const bool ghost = 2 * pt + static_cast<int>(rank) >= n_tiles;
+        if (main_warp && use > 0) {
+          mbar_wait(&hfree_bar[slot], (use - 1) & 1);                     // local dh pass done with the slot
+          if (lane == 0) wait_counter_ge(p.done + pair * p.NS + slot, static_cast<unsigned>(p.n_out * use));
+          __syncwarp();                                                    // consumers done with the slot
+        }
+        if (ghost) {
+          if (main_warp) {   // the empty half of an odd last pair-tile: zero rows
+            __nv_bfloat16* o = p.dz_ring + static_cast<size_t>(ring_row) * p.Vp;
+            const int n16 = kBM * p.Vp / 8;
+            for (int i = lane; i < n16; i += 32) st_cg_u4(o + static_cast<size_t>(i) * 8, make_uint4(0, 0, 0, 0));
+            __threadfence();
+            fence_proxy_async_global();
+            __syncwarp();
+          }
+        } else {
+          for (int k = 0; k < nbox; ++k, ++q) {
+            const int b = q % kZBoxes;
+            uint8_t* box = uni + zbox_offset(b);
+            mbar_wait(&zdone_bar[b], (q / kZBoxes) & 1);
+            if (main_warp && lane == 0) {
+              if (!(p.dbg & 2048)) tma_store_2d(&tm_dz, box, k * 64, ring_row);
+              tma_store_commit();
+            }
+            // db: column sums over this warp's 64 rows (lane owns columns 2*lane, 2*lane + 1 of the box)
+            if (!(p.dbg & 32)) {
+              const uint32_t colp = smem_u32(box) + (main_warp ? 0 : 8192) + (lane & 3) * 4;
+              const int ch = lane >> 2;
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 16
+              for (int rr = 0; rr < 64; rr += 2) {
+                const uint32_t w0 = lds32(colp + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                const uint32_t w1 = lds32(colp + (rr + 1) * 128 + ((ch ^ ((rr + 1) & 7)) << 4));
+                s0 += bf16lo(w0); s1 += bf16hi(w0);
+                s2 += bf16lo(w1); s3 += bf16hi(w1);
+              }
+              const int gcol = k * 64 + 2 * lane;
+              if (gcol < p.V) red_add_f32(p.db + gcol, s0 + s2);
+              if (gcol + 1 < p.V) red_add_f32(p.db + gcol + 1, s1 + s3);
+            }
+            __syncwarp();
+            if (main_warp) {
+              if (lane == 0) tma_store_wait_read0();       // the store has read the box
+              __syncwarp();
+              mbar_wait(&zempty_bar[b], (q / kZBoxes) & 1);  // so has warp 9
+              load_next(q + kZBoxes);
+            } else if (lane == 0) {
+              mbar_arrive(&zempty_bar[b]);
+            }
+          }
+        }
+        // the slot's dz rows are complete: hand it to the local dh pass and (one release per CTA) to the consumers
+        if (main_warp) {
+          if (lane == 0) {
+            tma_store_wait_all0();
+            mbar_arrive(&hfull_bar[slot]);
+            __threadfence();
+            red_release_gpu_add_u32(p.ready + pair * p.NS + slot, 1u);
+          }
+          __syncwarp();
+        }
       }
     }
   } else if (pair < p.P + p.C) {
@@ -1143,7 +1396,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       for (int pt = kg; pt < n_ptiles; pt += p.KG) {
         const int pp = pt % p.P, it = pt / p.P;
         const int slot = it % p.NS, use = it / p.NS;
-        { PCNT_BEGIN(a); wait_counter_ge(p.ready + pp * p.NS + slot, 16u * static_cast<unsigned>(use + 1)); PCNT_END(a, w_ready); }
+        { PCNT_BEGIN(a); wait_counter_ge(p.ready + pp * p.NS + slot, (keep ? 2u : 16u) * static_cast<unsigned>(use + 1)); PCNT_END(a, w_ready); }
         fence_proxy_async_global();
         const int row0 = (pp * p.NS + slot) * 2 * kBM;
         for (int kb = 0; kb < 4; ++kb) {
@@ -1157,11 +1410,19 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 #pragma unroll
             for (int q = 0; q < 2; ++q) tma_load_2d_pair_a(sa + q * 8192, &tm_dz_mn, &full_bar[s], v0 + q * 64, rr);
             if (!lockstep) {
+              // kept h: rows of the tile itself (k-blocks 0, 1 = first tile of the pair-tile, 2, 3 = second; the empty half
+              // of an odd last pair-tile reads the last tile: its dz rows are zero, h only has to be finite)
+              int hr = rr;
+              if (keep) {
+                int pos = 2 * pt + (kb >> 1);
+                pos = pos < n_tiles ? pos : n_tiles - 1;
+                hr = (p.active_tiles ? p.active_tiles[pos] : pos) * kBM + (kb & 1) * 64;
+              }
 #pragma unroll
-              for (int q = 0; q < 2; ++q) tma_load_2d_pair_a(sa + 16384 + q * 8192, &tm_h_mn, &full_bar[s], hx0 + q * 64, rr);
+              for (int q = 0; q < 2; ++q) tma_load_2d_pair_a(sa + 16384 + q * 8192, &tm_h_mn, &full_bar[s], hx0 + q * 64, hr);
               if (two) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q) tma_load_2d_pair_a(sa + 32768 + q * 8192, &tm_h_mn, &full_bar[s], hy0 + q * 64, rr);
+                for (int q = 0; q < 2; ++q) tma_load_2d_pair_a(sa + 32768 + q * 8192, &tm_h_mn, &full_bar[s], hy0 + q * 64, hr);
               }
             } else if (two) {      // pair 0 of the cluster fetches the X boxes, pair 1 the Y boxes; both multicast
               const uint32_t off = cpair ? 32768u : 16384u;
@@ -1320,9 +1581,18 @@ int max_ctas_fwd_persist(int csize, int hgen_warps) {
   return hgen_warps == 8 ? max_ctas_fwd_persist_t<8>(csize) : max_ctas_fwd_persist_t<4>(csize);
 }
 int read_persist_prof3(unsigned long long* out, int n, int reset) {
-  if (n > 160 * 8) n = 160 * 8;
-  if (cudaMemcpyFromSymbol(out, g_pprof3, sizeof(unsigned long long) * n) != cudaSuccess) return -1;
-  if (reset) { static unsigned long long z[160 * 8] = {}; cudaMemcpyToSymbol(g_pprof3, z, sizeof(z)); }
+  // n > 160 * 8: the second half is bank 4 (kept-logits dz pass)
+  const int n3 = n > 160 * 8 ? 160 * 8 : n;
+  if (cudaMemcpyFromSymbol(out, g_pprof3, sizeof(unsigned long long) * n3) != cudaSuccess) return -1;
+  if (n > n3) {
+    const int n4 = n - n3 > 160 * 8 ? 160 * 8 : n - n3;
+    if (cudaMemcpyFromSymbol(out + n3, g_pprof4, sizeof(unsigned long long) * n4) != cudaSuccess) return -1;
+  }
+  if (reset) {
+    static unsigned long long z[160 * 8] = {};
+    cudaMemcpyToSymbol(g_pprof3, z, sizeof(z));
+    cudaMemcpyToSymbol(g_pprof4, z, sizeof(z));
+  }
   return n;
 }
 int read_persist_prof(unsigned long long* out, int n) {
@@ -1334,8 +1604,8 @@ int read_persist_prof(unsigned long long* out, int n) {
 }
 
 template <int kHW>
-static void launch_fwd_persist_t(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
-                                 cudaStream_t s) {
+static void launch_fwd_persist_t(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const CUtensorMap& tm_z,
+                                 const FwdPArgs& a, int n_ctas, cudaStream_t s) {
   static bool configured[kMaxDevices] = {};
   if (bool& c = configured[current_device()]; !c) {
     cudaFuncSetAttribute(fwd_persist_kernel<kHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
@@ -1350,12 +1620,12 @@ static void launch_fwd_persist_t(const CUtensorMap& tm_hscratch, const CUtensorM
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = a.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, fwd_persist_kernel<kHW>, tm_hscratch, tm_w, a);
+  cudaLaunchKernelEx(&cfg, fwd_persist_kernel<kHW>, tm_hscratch, tm_w, tm_z, a);
 }
-void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const FwdPArgs& a, int n_ctas,
-                        cudaStream_t s) {
-  if (a.hgen_warps == 8) launch_fwd_persist_t<8>(tm_hscratch, tm_w, a, n_ctas, s);
-  else launch_fwd_persist_t<4>(tm_hscratch, tm_w, a, n_ctas, s);
+void launch_fwd_persist(const CUtensorMap& tm_hscratch, const CUtensorMap& tm_w, const CUtensorMap& tm_z, const FwdPArgs& a,
+                        int n_ctas, cudaStream_t s) {
+  if (a.hgen_warps == 8) launch_fwd_persist_t<8>(tm_hscratch, tm_w, tm_z, a, n_ctas, s);
+  else launch_fwd_persist_t<4>(tm_hscratch, tm_w, tm_z, a, n_ctas, s);
 }
 
 
@@ -1396,7 +1666,7 @@ void set_bwd_mega_cooperative(int v) { g_mega_cooperative = v != 0; }
 
 void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUtensorMap& tm_dz, const CUtensorMap& tm_wt,
                      const CUtensorMap& tm_dz_mn, const CUtensorMap& tm_h_mn, const CUtensorMap& tm_dz_st,
-                     const BwdPArgs& a, int n_ctas, cudaStream_t s) {
+                     const CUtensorMap& tm_zl, const BwdPArgs& a, int n_ctas, cudaStream_t s) {
   static bool configured[kMaxDevices] = {};
   bool& cooperative = g_mega_cooperative;   // the CTAs wait on one another: ask the driver to co-schedule the grid
   if (bool& c = configured[current_device()]; !c) {
@@ -1415,7 +1685,7 @@ void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUt
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (cooperative && !profiler_attached()) ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, bwd_mega_kernel, tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, bwd_mega_kernel, tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, tm_zl, a);
   if (cooperative && (e == cudaErrorNotSupported || e == cudaErrorInvalidValue)) {
     // cooperative + cluster launch not accepted by this driver / under this tool (a profiler replaying launches):
     // this ONE launch falls back to a plain launch -- the grid is sized to the co-resident capacity reported by
@@ -1424,7 +1694,7 @@ void launch_bwd_mega(const CUtensorMap& tm_h, const CUtensorMap& tm_w, const CUt
     // any other error is returned to the caller through cudaGetLastError().
     (void)cudaGetLastError();
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, bwd_mega_kernel, tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, a);
+    cudaLaunchKernelEx(&cfg, bwd_mega_kernel, tm_h, tm_w, tm_dz, tm_wt, tm_dz_mn, tm_h_mn, tm_dz_st, tm_zl, a);
   }
 }
 

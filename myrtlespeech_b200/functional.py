@@ -1,4 +1,5 @@
 """Autograd-level entry points over the C-ABI library (no torch types cross the boundary)."""
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -59,15 +60,42 @@ def _state_bytes(B, Tmax, Umax, V, H):
     return (_align1k(4 * (B + 1)) + 2 * _align1k(4 * B) + _align1k(4 * max_tiles * 128) + 4 * _align1k(4 * cells))
 
 
+#: Keep the joint's activations -- logits (fp16) and h = tanh(f + g) (bf16) -- from the forward to the backward call
+#: instead of recomputing them there: 6.8 GB per live graph at B=32 T=500 U=100 V=H=1024 against 2 of the 8 N*H*V flops of
+#: a step (include/rnnt_b200.h, ``rnnt_fused_forward_keep``).  ``RNNT_KEEP_ACTIVATIONS=0`` or
+#: ``set_keep_activations(False)`` selects the recompute schedule; so does an allocation that does not fit.
+_keep = os.environ.get("RNNT_KEEP_ACTIVATIONS", "1") != "0"
+
+
+def set_keep_activations(flag: bool) -> None:
+    """Choose between keeping logits and h for the backward pass (default) and recomputing them (less memory)."""
+    global _keep
+    _keep = bool(flag)
+
+
+def _kept_bytes(B, Tmax, Umax, V, H):
+    """``rnnt_fused_kept_bytes`` restated for symbolic sizes: per lattice tile 128 rows x (fp16 padded vocabulary + bf16 H);
+    nothing is kept for more than 4096 vocabulary columns (``tests/test_modules_cpu.py`` checks it against the library)."""
+    if not _keep:
+        return 0
+    Vp = (V + 63) // 64 * 64
+    if Vp > 4096:
+        return 0
+    max_tiles = B * ((Tmax + 15) // 16) * ((Umax + 1 + 7) // 8)
+    return _align1k(2 * max_tiles * 128 * Vp) + 2 * max_tiles * 128 * H
+
+
 def _bf16c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.bfloat16).contiguous()
 
 
 @torch.library.custom_op("rnnt_b200::fused_joint_loss", mutates_args=(), device_types="cuda")
 def _fused_joint_loss(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tensor,
-                      f_lens: torch.Tensor, y_lens: torch.Tensor, blank: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """``(loss (B,) fp32, state (rnnt_fused_state_bytes,) uint8)``: joint + log-softmax + alpha/beta through
-    ``rnnt_fused_forward``; ``state`` is what ``rnnt_b200::fused_joint_loss_backward`` needs back."""
+                      f_lens: torch.Tensor, y_lens: torch.Tensor, blank: int
+                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``(loss (B,) fp32, state (rnnt_fused_state_bytes,) uint8, kept (rnnt_fused_kept_bytes,) uint8)``: joint +
+    log-softmax + alpha/beta through ``rnnt_fused_forward_keep``; ``state`` and ``kept`` (empty when they are
+    recomputed instead of kept) are what ``rnnt_b200::fused_joint_loss_backward`` needs back."""
     lib = _lib.load()
     B, Tmax, H = f.shape
     Umax = g.shape[1] - 1
@@ -84,26 +112,34 @@ def _fused_joint_loss(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: O
         ws = _workspace(nbytes, f.device)
         ws[:sbytes].zero_()       # the per-cell arrays have cells no kernel writes (outside the lattice): keep them defined
         loss = torch.empty(B, dtype=torch.float32, device=f.device)
-        _lib.check(lib.rnnt_fused_forward(_ptr(fb), _ptr(gb), _ptr(Wb), _ptr(bf), _ptr(yi), _ptr(fl), _ptr(yl),
-                                          B, Tmax, Umax, V, H, int(blank), _ptr(loss), _ptr(ws), nbytes,
-                                          _stream(f.device)))
+        zbytes = _kept_bytes(B, Tmax, Umax, V, H)
+        try:
+            kept = torch.empty(zbytes, dtype=torch.uint8, device=f.device)
+        except torch.OutOfMemoryError:
+            kept = torch.empty(0, dtype=torch.uint8, device=f.device)
+        _lib.check(lib.rnnt_fused_forward_keep(_ptr(fb), _ptr(gb), _ptr(Wb), _ptr(bf), _ptr(yi), _ptr(fl), _ptr(yl),
+                                               B, Tmax, Umax, V, H, int(blank), _ptr(loss), _ptr(ws), nbytes,
+                                               _ptr(kept) if kept.numel() else None, kept.numel(),
+                                               _stream(f.device)))
         state = ws[:sbytes].clone()
-    return loss, state
+    return loss, state, kept
 
 
 @_fused_joint_loss.register_fake
 def _(f, g, W, bias, y, f_lens, y_lens, blank):
     B, Tmax, H = f.shape
     return (f.new_empty((B,), dtype=torch.float32),
-            f.new_empty((_state_bytes(B, Tmax, g.shape[1] - 1, W.shape[0], H),), dtype=torch.uint8))
+            f.new_empty((_state_bytes(B, Tmax, g.shape[1] - 1, W.shape[0], H),), dtype=torch.uint8),
+            f.new_empty((_kept_bytes(B, Tmax, g.shape[1] - 1, W.shape[0], H),), dtype=torch.uint8))
 
 
 @torch.library.custom_op("rnnt_b200::fused_joint_loss_backward", mutates_args=(), device_types="cuda")
 def _fused_joint_loss_backward(grad_loss: torch.Tensor, f: torch.Tensor, g: torch.Tensor, W: torch.Tensor,
                                bias: Optional[torch.Tensor], y: torch.Tensor, f_lens: torch.Tensor, y_lens: torch.Tensor,
-                               state: torch.Tensor, blank: int
+                               state: torch.Tensor, kept: torch.Tensor, blank: int
                                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """``(df, dg, dW, db)`` in fp32 through ``rnnt_fused_backward``; ``state`` is the forward op's second output."""
+    """``(df, dg, dW, db)`` in fp32 through ``rnnt_fused_backward_kept``; ``state`` and ``kept`` are the forward op's
+    second and third outputs."""
     lib = _lib.load()
     B, Tmax, H = f.shape
     Umax = g.shape[1] - 1
@@ -122,14 +158,15 @@ def _fused_joint_loss_backward(grad_loss: torch.Tensor, f: torch.Tensor, g: torc
     with _on(fb):
         ws = _workspace(nbytes, dev)
         ws[: state.numel()].copy_(state)
-        _lib.check(lib.rnnt_fused_backward(_ptr(fb), _ptr(gb), _ptr(Wb), _ptr(bf), _ptr(yi), _ptr(fl), _ptr(yl),
-                                           B, Tmax, Umax, V, H, int(blank), _ptr(gl), _ptr(df), _ptr(dg), _ptr(dW),
-                                           _ptr(db), _ptr(ws), nbytes, _stream(dev)))
+        _lib.check(lib.rnnt_fused_backward_kept(_ptr(fb), _ptr(gb), _ptr(Wb), _ptr(bf), _ptr(yi), _ptr(fl), _ptr(yl),
+                                                B, Tmax, Umax, V, H, int(blank), _ptr(gl), _ptr(df), _ptr(dg), _ptr(dW),
+                                                _ptr(db), _ptr(ws), nbytes,
+                                                _ptr(kept) if kept.numel() else None, kept.numel(), _stream(dev)))
     return df, dg, dW, db
 
 
 @_fused_joint_loss_backward.register_fake
-def _(grad_loss, f, g, W, bias, y, f_lens, y_lens, state, blank):
+def _(grad_loss, f, g, W, bias, y, f_lens, y_lens, state, kept, blank):
     B, Tmax, H = f.shape
     V = W.shape[0]
     new = lambda *shape: f.new_empty(shape, dtype=torch.float32)  # noqa: E731
@@ -138,16 +175,22 @@ def _(grad_loss, f, g, W, bias, y, f_lens, y_lens, state, blank):
 
 def _setup_context(ctx, inputs, output):
     f, g, W, bias, y, f_lens, y_lens, blank = inputs
-    _, state = output
-    ctx.save_for_backward(f, g, W, bias, y, f_lens, y_lens, state)
+    _, state, kept = output
+    ctx.save_for_backward(f, g, W, bias, y, f_lens, y_lens, state, kept)
+    # state and kept carry no gradient: without this autograd materialises zero "gradients" for them in every backward
+    # pass -- a 3.5 GB fill at the target shape (0.9 ms of a 10 ms step, measured)
+    ctx.mark_non_differentiable(state, kept)
+    ctx.set_materialize_grads(False)
     ctx.blank = blank
     ctx.has_bias = bias is not None
 
 
-def _backward(ctx, grad_loss, _grad_state):
-    f, g, W, bias, y, f_lens, y_lens, state = ctx.saved_tensors
+def _backward(ctx, grad_loss, _grad_state, _grad_kept):
+    f, g, W, bias, y, f_lens, y_lens, state, kept = ctx.saved_tensors
+    if grad_loss is None:
+        grad_loss = torch.zeros(f.shape[0], dtype=torch.float32, device=f.device)
     df, dg, dW, db = torch.ops.rnnt_b200.fused_joint_loss_backward(grad_loss, f, g, W, bias, y, f_lens, y_lens, state,
-                                                                    ctx.blank)
+                                                                    kept, ctx.blank)
     return (df.to(f.dtype), dg.to(g.dtype), dW.to(W.dtype), db.to(bias.dtype) if ctx.has_bias else None,
             None, None, None, None)
 
@@ -160,7 +203,8 @@ def rnnt_joint_loss(f: torch.Tensor, g: torch.Tensor, W: torch.Tensor, bias: Opt
     """Per-utterance ``-ln P(y|x)`` of the additive-tanh joint, fused with its lattice.
 
     f (B,T,H), g (B,U+1,H), W (V,H), bias (V) or None, y (B,U) int; returns (B,) fp32.
-    The (B,T,U+1,V) logits are never materialised.  The arithmetic is the registered operator
+    The (B,T,U+1,V) logits exist only as the fp16 copy kept for the backward pass (``set_keep_activations(False)``: never
+    materialised, recomputed there instead).  The arithmetic is the registered operator
     ``torch.ops.rnnt_b200.fused_joint_loss`` (CUDA only; fake implementation and autograd formula registered, so it
     traces under ``torch.compile`` / ``torch.export`` as one opaque node).
     """

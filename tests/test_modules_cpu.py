@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_workspace_arithmetic():
     lib = _lib.load()
-    assert lib.rnnt_abi_version() == 2
+    assert lib.rnnt_abi_version() == 3
     small = lib.rnnt_fused_workspace_bytes(4, 200, 50, 29, 512)
     big = lib.rnnt_fused_workspace_bytes(32, 500, 100, 1024, 1024)
     assert 0 < small < big < 1 << 30
@@ -53,6 +53,8 @@ def test_abi_version_and_workspace_arithmetic():
 def test_c_abi_rejects_bad_arguments_without_a_gpu():
     lib = _lib.load()
     rc = lib.rnnt_fused_forward(None, None, None, None, None, None, None, 1, 4, 2, 5, 8, 0, None, None, 0, None)
+    assert rc == 1 and b"NULL" in lib.rnnt_last_error()
+    rc = lib.rnnt_fused_forward_keep(None, None, None, None, None, None, None, 1, 4, 2, 5, 8, 0, None, None, 0, None, 0, None)
     assert rc == 1 and b"NULL" in lib.rnnt_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc)
@@ -229,13 +231,22 @@ def test_custom_op_is_registered_with_a_fake_implementation():
     for dims in [(32, 500, 100, 1024, 1024), (3, 37, 11, 300, 128), (1, 1, 0, 3, 8), (2, 6, 1100, 12, 8), (4, 200, 50, 29, 512)]:
         assert lib.rnnt_fused_state_bytes(*dims) == F._state_bytes(*dims), dims
         assert 0 < lib.rnnt_fused_state_bytes(*dims) < lib.rnnt_fused_workspace_bytes(*dims)
+        assert lib.rnnt_fused_kept_bytes(*dims) == F._kept_bytes(*dims) > 0, dims
+    assert lib.rnnt_fused_kept_bytes(32, 500, 100, 1024, 1024) == 2 * 13312 * 128 * (1024 + 1024)     # 6.98 GB at the target shape
+    assert lib.rnnt_fused_kept_bytes(4, 200, 50, 5000, 512) == F._kept_bytes(4, 200, 50, 5000, 512) == 0
+    F.set_keep_activations(False)
+    try:
+        assert F._kept_bytes(32, 500, 100, 1024, 1024) == 0
+    finally:
+        F.set_keep_activations(True)
     with FakeTensorMode():
         f = torch.empty(3, 37, 128, device="cuda"); g = torch.empty(3, 12, 128, device="cuda")
         W = torch.empty(300, 128, device="cuda"); b = torch.empty(300, device="cuda")
         y = torch.empty(3, 11, dtype=torch.int32, device="cuda")
         fl = torch.empty(3, dtype=torch.int64); yl = torch.empty(3, dtype=torch.int64)
-        loss, state = torch.ops.rnnt_b200.fused_joint_loss(f, g, W, b, y, fl, yl, 299)
+        loss, state, logits = torch.ops.rnnt_b200.fused_joint_loss(f, g, W, b, y, fl, yl, 299)
         assert tuple(loss.shape) == (3,) and loss.dtype == torch.float32 and loss.device.type == "cuda"
         assert state.dtype == torch.uint8 and state.numel() == F._state_bytes(3, 37, 11, 300, 128)
-        grads = torch.ops.rnnt_b200.fused_joint_loss_backward(loss, f, g, W, None, y, fl, yl, state, 299)
+        assert logits.dtype == torch.uint8 and logits.numel() == F._kept_bytes(3, 37, 11, 300, 128)
+        grads = torch.ops.rnnt_b200.fused_joint_loss_backward(loss, f, g, W, None, y, fl, yl, state, logits, 299)
         assert [tuple(t.shape) for t in grads] == [(3, 37, 128), (3, 12, 128), (300, 128), (300,)]
