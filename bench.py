@@ -218,6 +218,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the configs[4] greedy-decode measurement")
+    ap.add_argument("--recompute", action="store_true",
+                    help="recompute the joint's logits and h in the backward pass instead of keeping them from the forward pass "
+                         "(7 GB less memory per live graph at the target shape, about 10 %% slower)")
     ap.add_argument("--ragged", action="store_true",
                     help="SURVEY.md 8(d) secondary run: one global ragged batch, sharded by lattice size across the ranks")
     args = ap.parse_args()
@@ -255,6 +258,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     peaks = load_peaks()
+    from myrtlespeech_b200 import functional as Fk
+    if args.recompute:
+        Fk.set_keep_activations(False)
+    kept_bytes = int(Fk._kept_bytes(B, T, U, V, H))
 
     f, g, W, bias, y, fl, yl, balance = draw_batch(args, B, T, U, V, H, rank, world)
     if args.ragged:
@@ -433,8 +440,9 @@ def main():
         nhv = float(n_rows) * H * V
         flops = {"joint_fwd": 2.0 * nhv, "joint_dz": 0.0, "joint_dh": 2.0 * nhv, "joint_dw": 2.0 * nhv,
                  "joint_bwd_mega": 4.0 * nhv}
+        # executed by the hardware: the mega-kernel recomputes the logits (6NHV) unless the forward pass kept them (4NHV)
         hw_flops = {"joint_fwd": 2.0 * nhv, "joint_dz": 2.0 * nhv, "joint_dh": 2.0 * nhv, "joint_dw": 2.0 * nhv,
-                    "joint_bwd_mega": 6.0 * nhv}
+                    "joint_bwd_mega": (4.0 if kept_bytes else 6.0) * nhv}
         exec_frac = tiles["fraction"] if tiles else 1.0      # share of the lattice the backward pass executes
         kernels = {}
         for i, name in enumerate(KCLASSES):
@@ -471,7 +479,8 @@ def main():
                         "note": "achieved = algorithmic flops of the whole lattice (6NHV basis, logits recompute not counted) / mean "
                                 "in-loop CUDA-event duration of the launch.  The backward pass walks only the lattice tiles with "
                                 "non-zero arc occupancy (executed_fraction of them; the others contribute exact zeros): hw_achieved "
-                                "counts the flops actually executed, recompute GEMM included"}
+                                "counts the flops actually executed (with --recompute that includes the logits GEMM; by default "
+                                "the forward pass keeps logits and h and the backward pass executes 4NHV)"}
         else:
             # V=29, H=512: 0.03 flop per byte of tanh input on the tensor side -- the path is bound by the special-function
             # work (one tanh per row and column of h in each pass, one exp2 per logit in each pass), not by tensor cores
@@ -530,6 +539,10 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline,
             "kernels": kernels,
+            "activations": {"schedule": "kept" if kept_bytes else "recomputed", "kept_bytes_per_live_graph": kept_bytes,
+                            "note": "kept: the forward pass also writes the logits (fp16) and h (bf16) of every lattice row and the "
+                                    "backward pass streams them back; recomputed (--recompute): nothing is kept, the backward pass "
+                                    "rebuilds h and the logits"},
             "backward_tiles": tiles,
             "ms_per_step_every_tile": None if no_skip_ms is None else round(no_skip_ms, 4),
             "value_every_tile": None if no_skip_ms is None else round(Bl * world / (no_skip_ms * 1e-3), 2),
@@ -539,7 +552,7 @@ def main():
             "kernels_isolated_ms": iso,
             "kernels_sum_ms": round(ksum, 4),
             "unattributed_ms": round(step_ms - ksum, 4),
-            "unattributed_note": "step time minus the kernel classes: four output memsets (df, dg, dW, db), the 38 MB state "
+            "unattributed_note": "step time minus the kernel classes: four output memsets (df, dg, dW, db), the state "
                                  "prefix zero / save / restore copies, loss.sum and the autograd glue kernels, launch gaps",
             "cpu_baseline": cpu,
             "clocks": clocks,

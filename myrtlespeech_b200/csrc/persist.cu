@@ -583,7 +583,8 @@ __device__ __forceinline__ uint4 ld_ca_u4(const void* ptr) {
 __device__ __forceinline__ void tma_store_wait_all1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
 
-constexpr int kMegaThreads = 512;  // 16 warps, roles above (warps 8, 9 idle)
+constexpr int kMegaThreads = 512;  // 16 warps: 0..7 epilogue, 8..11 hgen / dz transform (one per scheduler), 12 TMA, 13 MMA,
+                                   // 14, 15 post warps of the kept-logits schedule (idle otherwise)
 
 // ---- dh-pass reductions in registers -------------------------------------------------------------------
 // A producer epilogue warp holds 32 tile rows: lane = 8 * (frame & 3) + label position.  df sums a column over
@@ -636,13 +637,13 @@ __device__ __forceinline__ void reduce_over_frames(const float (&v)[32], int lan
 // When the forward pass stored the base-2 logits z2 = log2(e) (W h + bias) as fp16, dz = c0 2^(z2 - lse2) - [blank] c1 -
 // [label] c2 is a streaming pass: no recompute GEMM, no TMEM round trip.  Three warp roles share a ring of three
 // 128-row x 64-column boxes (16 KB, 128-byte swizzle) in shared memory:
-//   * post warp 8 TMA-loads the tile's logits box by box (mbarrier completion -- register prefetch cannot cover the
+//   * post warp 14 TMA-loads the tile's logits box by box (mbarrier completion -- register prefetch cannot cover the
 //     latency: a warp's loads share six scoreboards, so waiting for the oldest load waits for the youngest on the same
 //     counter: measured 700 cycles per row),
-//   * the 128 transform threads (warps 10, 11, 14, 15) each own one lattice row (row scalars in registers) and turn a box
+//   * the 128 transform threads (warps 8..11, one per scheduler and MUFU unit) each own one lattice row (row scalars in registers) and turn a box
 //     into bf16 dz IN PLACE (conflict-free 16-byte accesses under the swizzle); the two special columns take their exact
 //     fp32 values (lp_blank / lp_label), as in the recompute path,
-//   * post warps 8 and 9 TMA-store the box into the ring slot, add its column sums (db, from the staged bf16 values, as in
+//   * post warps 14 and 15 TMA-store the box into the ring slot, add its column sums (db, from the staged bf16 values, as in
 //     the recompute path) and recycle the buffer.
 // The transform warps never touch the ring slot, so they run ahead of the slot's reuse by the depth of the box ring.
 constexpr int kZBoxBytes = kBM * 64 * 2;   // 16 KB
@@ -753,9 +754,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   uint64_t* hfree_bar = bars + 16;                // [kMaxNS] epilogue (dh pass finished with the slot's h) -> hgen
   uint64_t* dzr_bar = bars + 20;                  // [kMaxVChunks] dz chunk stored and visible -> TMA (dh pass)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20 + kMaxVChunks);
-  uint64_t* zfull_bar = bars + 21 + kMaxVChunks;    // [kZBoxes] kept logits: post warp 8 (TMA load) -> transform warps
+  uint64_t* zfull_bar = bars + 21 + kMaxVChunks;    // [kZBoxes] kept logits: post warp 14 (TMA load) -> transform warps
   uint64_t* zdone_bar = bars + 24 + kMaxVChunks;    // [kZBoxes] transform warps (4) -> post warps: box holds dz
-  uint64_t* zempty_bar = bars + 27 + kMaxVChunks;   // [kZBoxes] post warp 9 -> post warp 8: box read, may be refilled
+  uint64_t* zempty_bar = bars + 27 + kMaxVChunks;   // [kZBoxes] post warp 15 -> post warp 14: box read, may be refilled
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -785,7 +786,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], lockstep ? 2 : 1); }
     // producers: 8 epilogue warps per CTA; consumers: 4 flush warps per CTA (periodic flush of the dW accumulators)
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], is_producer ? 16 : 8); }
-    // kept logits: a slot is "full" when post warp 8 has stored its dz rows (its h is not in the ring at all)
+    // kept logits: a slot is "full" when post warp 14 has stored its dz rows (its h is not in the ring at all)
     for (int i = 0; i < kMaxNS; ++i) { mbar_init(&hfull_bar[i], p.zlog ? 1 : kHgenThreads); mbar_init(&hfree_bar[i], 8); }
     for (int i = 0; i < kMaxVChunks; ++i) mbar_init(&dzr_bar[i], 8);
     for (int i = 0; i < kZBoxes; ++i) {
@@ -1240,9 +1241,11 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                       (static_cast<unsigned long long>(ep_hold_dh >> 10) << 16) | static_cast<unsigned long long>(ep_tot_dh >> 10);
       }
 #endif
-    } else if (warp >= 10) {
-      // ------------------------------- hgen (warps 10, 11, 14, 15) --------------------
-      const int ht = ((warp & 1) + ((warp >> 2) & 1) * 2) * 32 + lane;   // 10->0, 11->1, 14->2, 15->3
+    } else if (warp < 12) {
+      // ------------------------------- hgen / dz transform (warps 8..11) --------------------
+      // One warp per scheduler, i.e. per MUFU unit.  (Until round 2 these were warps 10, 11, 14, 15 -- two schedulers with
+      // two of them each and two with none: hgen took 33 k cycles per tile in the kernel against 17 k in isolation.)
+      const int ht = (warp - 8) * 32 + lane;
       int it = 0;
       TileCursor cur;
       cur.init(p.L);
@@ -1282,14 +1285,14 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       }
       }
     } else if (keep) {
-      // ------------------------------- post warps 8, 9 (kept logits) --------------------
-      // Warp 8: loads the logit boxes, stores the dz boxes, owns the ring slot's hand-over (slot free -> slot full ->
-      // consumers); warps 8 and 9 add db from rows 0..63 / 64..127 of each box.
-      const bool main_warp = warp == 8;
+      // ------------------------------- post warps 14, 15 (kept logits) --------------------
+      // Warp 14: loads the logit boxes, stores the dz boxes, owns the ring slot's hand-over (slot free -> slot full ->
+      // consumers); warps 14 and 15 add db from rows 0..63 / 64..127 of each box.
+      const bool main_warp = warp == 14;
       const int nbox = p.Vp >> 6;
       // loader cursor: the box that is loaded next (position in this CTA's tile sequence, box inside the tile)
       int l_pt = pair, l_k = 0;
-      auto load_next = [&](int ql) {      // warp 8, converged: issue the load of box number ql into buffer ql % kZBoxes
+      auto load_next = [&](int ql) {      // warp 14, converged: issue the load of box number ql into buffer ql % kZBoxes
         while (l_pt < n_ptiles && 2 * l_pt + static_cast<int>(rank) >= n_tiles) l_pt += p.P;   // skip the empty half
         if (l_pt >= n_ptiles) return;
         if (elect_one()) {
@@ -1352,7 +1355,7 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             if (main_warp) {
               if (lane == 0) tma_store_wait_read0();       // the store has read the box
               __syncwarp();
-              mbar_wait(&zempty_bar[b], (q / kZBoxes) & 1);  // so has warp 9
+              mbar_wait(&zempty_bar[b], (q / kZBoxes) & 1);  // so has warp 15
               load_next(q + kZBoxes);
             } else if (lane == 0) {
               mbar_arrive(&zempty_bar[b]);

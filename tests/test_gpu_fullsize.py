@@ -123,17 +123,19 @@ def _record(key, errs):
         pass
 
 
-@pytest.mark.parametrize("schedule", ["persistent", "slab"])
+@pytest.mark.parametrize("schedule", ["persistent", "recompute", "slab"])
 @pytest.mark.parametrize("name,ragged", [("configs1_chars", False), ("configs2_subword", False), ("target", False),
                                          ("target", True)])
 def test_full_size_matches_fp64_reference(name, ragged, schedule):
-    from myrtlespeech_b200 import _lib
+    from myrtlespeech_b200 import _lib, functional as F
     lib = _lib.load()
-    lib.rnnt_debug_set(b"path", 1 if schedule == "persistent" else 0)
+    lib.rnnt_debug_set(b"path", 0 if schedule == "slab" else 1)
+    F.set_keep_activations(schedule == "persistent")     # "persistent": activations kept (the default); "recompute": not
     try:
         got = _cuda(name, ragged)
     finally:
         lib.rnnt_debug_set(b"path", 1)
+        F.set_keep_activations(True)
     ref = _reference(name, ragged)
     errs = _errors(got, ref)
     _record(f"{name}{'_ragged' if ragged else ''}/{schedule}", errs)

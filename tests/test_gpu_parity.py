@@ -21,15 +21,18 @@ from oracle import rnnt_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["persistent", "slab"], autouse=True)
+@pytest.fixture(params=["persistent", "recompute", "slab"], autouse=True)
 def kernel_path(request):
-    """Every test runs on both schedules of the C-ABI library: the persistent kernels (one forward launch, one
-    backward mega-kernel; the default) and the per-slab kernels (the general fallback)."""
-    from myrtlespeech_b200 import _lib
+    """Every test runs on the three schedules of the C-ABI library: the persistent kernels with the joint's activations
+    kept for the backward pass (one forward launch, one backward mega-kernel; the default), the same kernels recomputing
+    the activations in the backward pass, and the per-slab kernels (the general fallback)."""
+    from myrtlespeech_b200 import _lib, functional as F
     lib = _lib.load()
-    lib.rnnt_debug_set(b"path", 1 if request.param == "persistent" else 0)
+    lib.rnnt_debug_set(b"path", 0 if request.param == "slab" else 1)
+    F.set_keep_activations(request.param == "persistent")
     yield request.param
     lib.rnnt_debug_set(b"path", 1)
+    F.set_keep_activations(True)
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-3
@@ -311,21 +314,35 @@ def test_subword_width_against_torchaudio():
         assert rel(got[name], t.grad.cpu().numpy()) < 2e-2, name
 
 
-def test_custom_op_passes_opcheck():
+def test_custom_op_passes_opcheck(kernel_path):
     """``torch.library.opcheck`` on the registered operator: schema (no undeclared mutation or aliasing), autograd
     registration, fake-tensor implementation against the real one, and eager vs AOT-dispatched outputs and gradients with
-    dynamic shapes.  Gradients are accumulated with fp32 atomics whose order differs run to run, hence the tolerances."""
+    dynamic shapes.  Gradients are accumulated with fp32 atomics whose order differs run to run, hence the tolerances.
+    opcheck compares every output, the opaque ``kept`` buffer included; its bytes are defined only where the forward
+    pass writes (the tiles of the batch, the vocabulary columns that exist), so the ragged cases run with the activations
+    recomputed (``kept`` is empty) and a dense batch with a 64-column vocabulary checks the kept schedule."""
+    from myrtlespeech_b200 import functional as F
     cfg = (23, 3, 14, 5, 29, 64, 28, True)
     f, g, W, bias, y, fl, yl = make(*cfg)
-    args = (f.cuda().requires_grad_(True), g.cuda().requires_grad_(True), W.cuda().requires_grad_(True),
-            bias.cuda().requires_grad_(True), y.cuda(), torch.tensor(fl), torch.tensor(yl), 28)
-    res = torch.library.opcheck(torch.ops.rnnt_b200.fused_joint_loss, args, atol=1e-5, rtol=1e-3)
-    assert all(v == "SUCCESS" for v in res.values()), res
-    # no bias; bf16 leaves (the gradients come back in the leaves' dtype)
-    args = (f.bfloat16().cuda().requires_grad_(True), g.bfloat16().cuda().requires_grad_(True),
-            W.bfloat16().cuda().requires_grad_(True), None, y.cuda(), torch.tensor(fl), torch.tensor(yl), 28)
-    res = torch.library.opcheck(torch.ops.rnnt_b200.fused_joint_loss, args, atol=1e-2, rtol=2e-2)
-    assert all(v == "SUCCESS" for v in res.values()), res
+    F.set_keep_activations(False)
+    try:
+        args = (f.cuda().requires_grad_(True), g.cuda().requires_grad_(True), W.cuda().requires_grad_(True),
+                bias.cuda().requires_grad_(True), y.cuda(), torch.tensor(fl), torch.tensor(yl), 28)
+        res = torch.library.opcheck(torch.ops.rnnt_b200.fused_joint_loss, args, atol=1e-5, rtol=1e-3)
+        assert all(v == "SUCCESS" for v in res.values()), res
+        # no bias; bf16 leaves (the gradients come back in the leaves' dtype)
+        args = (f.bfloat16().cuda().requires_grad_(True), g.bfloat16().cuda().requires_grad_(True),
+                W.bfloat16().cuda().requires_grad_(True), None, y.cuda(), torch.tensor(fl), torch.tensor(yl), 28)
+        res = torch.library.opcheck(torch.ops.rnnt_b200.fused_joint_loss, args, atol=1e-2, rtol=2e-2)
+        assert all(v == "SUCCESS" for v in res.values()), res
+    finally:
+        F.set_keep_activations(kernel_path == "persistent")
+    if kernel_path == "persistent":
+        f, g, W, bias, y, fl, yl = make(24, 2, 16, 7, 64, 64, 63, False)     # every tile and every column of `kept` is written
+        args = (f.cuda().requires_grad_(True), g.cuda().requires_grad_(True), W.cuda().requires_grad_(True),
+                bias.cuda().requires_grad_(True), y.cuda(), torch.tensor(fl), torch.tensor(yl), 63)
+        res = torch.library.opcheck(torch.ops.rnnt_b200.fused_joint_loss, args, atol=1e-5, rtol=1e-3)
+        assert all(v == "SUCCESS" for v in res.values()), res
 
 
 def test_fused_op_under_torch_compile_matches_eager():
@@ -370,7 +387,7 @@ def test_backward_walks_only_tiles_with_occupancy_and_loses_nothing(kernel_path)
     is zero costs no tiles at all."""
     import ctypes
     from myrtlespeech_b200 import _lib, functional as F
-    if kernel_path != "persistent":
+    if kernel_path == "slab":
         pytest.skip("the tile list belongs to the persistent backward kernel")
     lib = _lib.load()
     B, T, U, V, H = 3, 300, 60, 64, 64
@@ -399,3 +416,83 @@ def test_backward_walks_only_tiles_with_occupancy_and_loses_nothing(kernel_path)
                             faithful=True)
     for k in ("df", "dg", "dW", "db"):
         assert rel(out[0][k], ref[k]) < TOL, k
+
+
+@pytest.mark.parametrize("shape", [
+    (3, 37, 11, 300, 128),      # vocabulary ends inside a 64-column box and inside a 256-column chunk
+    (5, 70, 23, 1000, 520),     # H not a multiple of 64
+    (1, 16, 7, 29, 512),        # a single tile: the pair-tile's second half is empty
+    (3, 50, 20, 29, 512),       # narrow vocabulary: one logit box per tile, the box ring spans several tiles
+    (2, 130, 40, 2048, 256),    # 32 boxes per tile
+    (2, 40, 9, 4096, 64),       # widest vocabulary that is kept
+])
+def test_kept_activations_match_recompute(shape, kernel_path):
+    """Keeping logits (fp16) and h (bf16) for the backward pass against recomputing them there: same loss bit for bit (the
+    forward arithmetic is the same), gradients equal up to the fp16 rounding of the kept logits -- far inside the bf16
+    rounding of dz both schedules share -- and both within tolerance of the oracle."""
+    from myrtlespeech_b200 import _lib, functional as F
+    if kernel_path != "persistent":
+        pytest.skip("compares the two persistent schedules")
+    B, T, U, V, H = shape
+    f, g, W, bias, y, fl, yl = make(77, B, T, U, V, H, V - 1, True)
+    gl = list(np.linspace(0.5, 1.5, B))
+    lib = _lib.load()
+    assert lib.rnnt_fused_kept_bytes(B, T, U, V, H) > 0
+    out = {}
+    for keep in (True, False):
+        F.set_keep_activations(keep)
+        try:
+            out[keep] = run_cuda(f, g, W, bias, y, fl, yl, V - 1, grad_loss=gl)
+        finally:
+            F.set_keep_activations(True)
+    assert np.array_equal(out[True]["loss"], out[False]["loss"])
+    for k in ("df", "dg", "dW", "db"):
+        assert rel(out[True][k], out[False][k]) < 2e-4, (k, rel(out[True][k], out[False][k]))
+    ref = O.rnnt_joint_loss(f.numpy(), g.numpy(), W.numpy(), bias.numpy(), y.numpy(), fl, yl, V - 1, grad_loss=np.array(gl),
+                            faithful=True)
+    for k in ("df", "dg", "dW", "db"):
+        assert rel(out[True][k], ref[k]) < TOL, (k, rel(out[True][k], ref[k]))
+
+
+def test_kept_buffer_is_optional_at_the_c_abi(kernel_path):
+    """``rnnt_fused_forward_keep`` / ``rnnt_fused_backward_kept`` with a NULL buffer are ``rnnt_fused_forward`` /
+    ``rnnt_fused_backward``; with a buffer the backward call reads what the forward call kept, and a negative upstream
+    gradient flips every sign (the kept schedule carries the row scale in an exponent and the sign separately)."""
+    from myrtlespeech_b200 import _lib
+    if kernel_path != "persistent":
+        pytest.skip("C-ABI check of the kept-activation entry points")
+    lib = _lib.load()
+    B, T, U, V, H = 2, 40, 12, 70, 64
+    f, g, W, bias, y, fl, yl = make(5, B, T, U, V, H, V - 1, True)
+    dev = torch.device("cuda")
+    fb, gb, Wb = f.to(dev).bfloat16(), g.to(dev).bfloat16(), W.to(dev).bfloat16()
+    bf_, yi = bias.to(dev), y.to(dev).int()
+    fli, yli = torch.tensor(fl, dtype=torch.int32), torch.tensor(yl, dtype=torch.int32)
+    nbytes = lib.rnnt_fused_workspace_bytes(B, T, U, V, H)
+    kbytes = lib.rnnt_fused_kept_bytes(B, T, U, V, H)
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for name, kept, sign in (("null", None, 1.0), ("kept", torch.empty(kbytes, dtype=torch.uint8, device=dev), 1.0),
+                             ("negative", torch.empty(kbytes, dtype=torch.uint8, device=dev), -1.0)):
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty(B, device=dev)
+        kp, kn = (None, 0) if kept is None else (kept.data_ptr(), kbytes)
+        _lib.check(lib.rnnt_fused_forward_keep(fb.data_ptr(), gb.data_ptr(), Wb.data_ptr(), bf_.data_ptr(), yi.data_ptr(),
+                                               fli.data_ptr(), yli.data_ptr(), B, T, U, V, H, V - 1, loss.data_ptr(),
+                                               ws.data_ptr(), nbytes, kp, kn, st))
+        gl = torch.full((B,), sign, device=dev)
+        df = torch.empty(B, T, H, device=dev); dg = torch.empty(B, U + 1, H, device=dev)
+        dW = torch.empty(V, H, device=dev); db = torch.empty(V, device=dev)
+        _lib.check(lib.rnnt_fused_backward_kept(fb.data_ptr(), gb.data_ptr(), Wb.data_ptr(), bf_.data_ptr(), yi.data_ptr(),
+                                                fli.data_ptr(), yli.data_ptr(), B, T, U, V, H, V - 1, gl.data_ptr(),
+                                                df.data_ptr(), dg.data_ptr(), dW.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                                nbytes, kp, kn, st))
+        torch.cuda.synchronize()
+        res[name] = [t.cpu().numpy() for t in (loss, df, dg, dW, db)]
+    ref = O.rnnt_joint_loss(f.numpy(), g.numpy(), W.numpy(), bias.numpy(), y.numpy(), fl, yl, V - 1, faithful=True)
+    for name in ("null", "kept"):
+        assert rel(res[name][0], ref["loss"]) < TOL
+        for got, k in zip(res[name][1:], ("df", "dg", "dW", "db")):
+            assert rel(got, ref[k]) < TOL, (name, k)
+    for a, b in zip(res["kept"][1:], res["negative"][1:]):
+        assert rel(-b, a) < 1e-6
