@@ -410,6 +410,7 @@ def main():
     # exact zeros and are skipped; `prune = -1` walks every tile: timed here for comparison on a short loop) ----
     tiles = None
     no_skip_ms = None
+    skip_ab_ms = None
     if rank == 0:
         from myrtlespeech_b200 import functional as Fn
         ws = Fn._ws_pool.get((dev, torch.cuda.current_stream(dev).cuda_stream))
@@ -417,11 +418,18 @@ def main():
             n2 = (ctypes.c_int * 2)()
             if lib.rnnt_debug_read_active_tiles(ws.data_ptr(), Bl, fd.shape[1], gd.shape[1] - 1, V, H, n2) == 0 and n2[1] > 0:
                 tiles = {"walked": int(n2[0]), "total": int(n2[1]), "fraction": round(n2[0] / n2[1], 4)}
-        lib.rnnt_debug_set(b"prune", -1)
+        # A/B in alternating blocks (the part's thermal state drifts by several per cent over a run: a single block timed
+        # after the main loop compares two different clocks, not two schedules)
+        ab = {0: 0.0, -1: 0.0}
         for _ in range(3):
-            hot_step()
-        no_skip_ms = timed(hot_step, 10) / 10
+            for mode in (-1, 0):
+                lib.rnnt_debug_set(b"prune", mode)
+                for _ in range(2):
+                    hot_step()
+                ab[mode] += timed(hot_step, 5)
         lib.rnnt_debug_set(b"prune", 0)
+        no_skip_ms = ab[-1] / 15
+        skip_ab_ms = ab[0] / 15
     barrier()
 
     n_rows_local = int((fl.long() * (yl.long() + 1)).sum())
@@ -546,9 +554,12 @@ def main():
             "backward_tiles": tiles,
             "ms_per_step_every_tile": None if no_skip_ms is None else round(no_skip_ms, 4),
             "value_every_tile": None if no_skip_ms is None else round(Bl * world / (no_skip_ms * 1e-3), 2),
+            "ms_per_step_tile_list_ab": None if skip_ab_ms is None else round(skip_ab_ms, 4),
             "tile_skipping_note": "the backward pass skips lattice tiles whose arc occupancies are all exactly zero in fp32 (their "
                                   "gradient contribution is exactly zero, results are identical); *_every_tile is the same step with "
-                                  "the skipping switched off (rank 0, 10 steps after the main loop)",
+                                  "the skipping switched off and ms_per_step_tile_list_ab the default step, both measured on rank 0 "
+                                  "after the main loop in alternating blocks of 5 steps (3 blocks each), so that the two share one "
+                                  "thermal state",
             "kernels_isolated_ms": iso,
             "kernels_sum_ms": round(ksum, 4),
             "unattributed_ms": round(step_ms - ksum, 4),

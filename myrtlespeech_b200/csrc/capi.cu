@@ -128,7 +128,7 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
   p.o_beta = take(sizeof(double) * cells);
   p.o_lnpb = take(sizeof(float) * B);
   p.o_lnp64 = take(sizeof(double) * B);
-  p.o_wt = take(2 * static_cast<size_t>(H) * p.Vp);
+  p.o_wt = take(2 * align_up(H, 32) * p.Vp);       // W^T, rows padded to whole groups of 32 (joint.cu::transpose_w_kernel)
   p.o_h = take(2 * static_cast<size_t>(p.slab_tiles) * kTileRows * H);
   p.o_dz = take(2 * static_cast<size_t>(p.slab_tiles) * kTileRows * p.Vp);
   p.o_hs = take(2 * static_cast<size_t>(kMaxPersistCtas) * 2 * kTileRows * H);
@@ -144,14 +144,14 @@ Plan make_plan(int B, int Tmax, int Umax, int V, int H) {
     const double kb_h = (H + 63) / 64, kb_v = p.Vp / 64;
     const double ch_v = (p.Vp + 255) / 256, ch_h = (H + 255) / 256;
     const double mma_p = (ch_v * kb_h + ch_h * kb_v) * 4 * 128;
-    const double epi_p = 8000.0 * p.Vp / 256 + 10500.0 * H / 256;
+    const double epi_p = 8000.0 * p.Vp / 256 + 8800.0 * H / 256;
     const double prod = mma_p > epi_p ? mma_p : epi_p;
     double cons = 0;   // per block: 4 k-blocks x (1 or 2 accumulators) x 4 MMAs
     for (int hb = 0; hb < p.n_ht; ++hb) cons += p.n_vt * 4 * ((H - hb * 512 > 256) ? 8 : 4) * 128.0;
     const double c_ideal = (kMaxPersistCtas / 2) * cons / (cons + prod);
     p.KG = static_cast<int>(c_ideal / p.n_out + 0.5);
     // kept logits: the producers run the dh pass only (dz is a streaming pass of the front-end warps)
-    const double mma_k = ch_h * kb_v * 4 * 128, epi_k = 10500.0 * H / 256;
+    const double mma_k = ch_h * kb_v * 4 * 128, epi_k = 8800.0 * H / 256;
     const double prod_k = mma_k > epi_k ? mma_k : epi_k;
     p.KGk = static_cast<int>((kMaxPersistCtas / 2) * cons / (cons + prod_k) / p.n_out + 0.5);
   }
@@ -619,12 +619,15 @@ static int fused_backward_impl(const void* f, const void* g, const void* W, cons
   CUDA_TRY(cudaMemsetAsync(dg, 0, sizeof(float) * static_cast<size_t>(B) * (Umax + 1) * H, s));
   CUDA_TRY(cudaMemsetAsync(dW, 0, sizeof(float) * static_cast<size_t>(V) * H, s));
   CUDA_TRY(cudaMemsetAsync(db, 0, sizeof(float) * V, s));
-  KLAUNCH(K_MISC, s, launch_transpose_w(static_cast<const __nv_bfloat16*>(W), w.at<__nv_bfloat16>(p.o_wt), V, H, p.Vp, s));
 
   const int nc_v = chunk_cols(V), nc_h = chunk_cols(H);
   const bool keep = keeps_activations(p, kept, kept_bytes);
   const int n_cons = keep ? p.Ck : p.C, n_kg = keep ? p.KGk : p.KG;
-  if (g_path == 1 && p.mega_ok && max_ctas_bwd_mega(2) >= 2 * (p.P + p.C)) {
+  const bool mega = g_path == 1 && p.mega_ok && max_ctas_bwd_mega(2) >= 2 * (p.P + p.C);
+  const uint64_t wt_rows = align_up(H, 32);
+  // the mega-kernel wants the rows of W^T permuted inside groups of 32 (fragment layout of its dh epilogue)
+  KLAUNCH(K_MISC, s, launch_transpose_w(static_cast<const __nv_bfloat16*>(W), w.at<__nv_bfloat16>(p.o_wt), V, H, p.Vp, mega ? 1 : 0, s));
+  if (mega) {
     // 4-clusters (operand multicast between two pairs of one role): both roles must start on a cluster boundary,
     // both W chunk widths must split into quarters, and only the co-resident capacity for 4-clusters (132 of 148
     // CTAs on this part) can be used, so the producers give up the difference.
@@ -643,7 +646,7 @@ static int fused_backward_impl(const void* f, const void* g, const void* W, cons
     if ((rc = make_map(&tm_h, w.at<void>(p.o_hring), H, ring_rows, H, 64, 128))) return rc;
     if ((rc = make_map(&tm_w, W, H, V, H, 64, nc_v / wdiv))) return rc;
     if ((rc = make_map(&tm_dz, w.at<void>(p.o_dzring), p.Vp, ring_rows, p.Vp, 64, 128))) return rc;
-    if ((rc = make_map(&tm_wt, w.at<void>(p.o_wt), p.Vp, H, p.Vp, 64, nc_h / wdiv))) return rc;
+    if ((rc = make_map(&tm_wt, w.at<void>(p.o_wt), p.Vp, wt_rows, p.Vp, 64, nc_h / wdiv))) return rc;
     if ((rc = make_map(&tm_dz_mn, w.at<void>(p.o_dzring), p.Vp, ring_rows, p.Vp, 64, 64))) return rc;
     if ((rc = make_map(&tm_h_mn, w.at<void>(p.o_hring), H, ring_rows, H, 64, 64))) return rc;
     const size_t n_flags = static_cast<size_t>(kMaxPersistCtas / 2) * kMaxRingSlots;
@@ -686,7 +689,7 @@ static int fused_backward_impl(const void* f, const void* g, const void* W, cons
   if ((rc = make_map(&tm_h, w.at<void>(p.o_h), H, slab_rows, H, 64, 128))) return rc;
   if ((rc = make_map(&tm_w, W, H, V, H, 64, nc_v / 2))) return rc;
   if ((rc = make_map(&tm_dz, w.at<void>(p.o_dz), p.Vp, slab_rows, p.Vp, 64, 128))) return rc;
-  if ((rc = make_map(&tm_wt, w.at<void>(p.o_wt), p.Vp, H, p.Vp, 64, nc_h / 2))) return rc;
+  if ((rc = make_map(&tm_wt, w.at<void>(p.o_wt), p.Vp, wt_rows, p.Vp, 64, nc_h / 2))) return rc;
   if ((rc = make_map(&tm_dz_mn, w.at<void>(p.o_dz), p.Vp, slab_rows, p.Vp, 64, 64))) return rc;
   if ((rc = make_map(&tm_h_mn, w.at<void>(p.o_h), H, slab_rows, H, 64, 64))) return rc;
 

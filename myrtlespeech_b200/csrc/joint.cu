@@ -683,8 +683,12 @@ hgen_kernel(Lattice L, const __nv_bfloat16* __restrict__ f, const __nv_bfloat16*
   }
 }
 
+// Wt has ceil(H / 32) * 32 rows (rows >= H are zero).  perm != 0: inside every group of 32 rows, row 8 a + 2 c + e holds
+// column 8 c + 2 a + e of W (a, c = 0..3, e = 0, 1) -- the backward mega-kernel reads its dh accumulator in the 16x256b
+// fragment layout, where a thread owns accumulator columns 8 a + 2 c + {0, 1}: with the rows of the B operand permuted like
+// this those are eight CONTIGUOUS columns of H (8 c .. 8 c + 7), one 16-byte access for h, df and dg each.
 __global__ void transpose_w_kernel(const __nv_bfloat16* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int V,
-                                   int H, int Vp) {
+                                   int H, int Vp, int perm) {
   __shared__ __nv_bfloat16 t[32][33];
   const int v0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -693,8 +697,9 @@ __global__ void transpose_w_kernel(const __nv_bfloat16* __restrict__ W, __nv_bfl
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int h = h0 + i, v = v0 + threadIdx.x;
-    if (h < H && v < Vp) Wt[static_cast<size_t>(h) * Vp + v] = t[threadIdx.x][i];
+    const int v = v0 + threadIdx.x;
+    const int src = perm ? (((i >> 1) & 3) << 3 | (i >> 3) << 1 | (i & 1)) : i;
+    if (v < Vp) Wt[static_cast<size_t>(h0 + i) * Vp + v] = t[threadIdx.x][src];
   }
 }
 
@@ -851,9 +856,9 @@ void launch_hgen(const Lattice& L, const __nv_bfloat16* f, const __nv_bfloat16* 
   hgen_kernel<<<n_tiles * (kTileRows / 8), 256, 0, s>>>(L, f, g, hslab, tile0, H);
 }
 
-void launch_transpose_w(const __nv_bfloat16* W, __nv_bfloat16* Wt, int V, int H, int Vp, cudaStream_t s) {
+void launch_transpose_w(const __nv_bfloat16* W, __nv_bfloat16* Wt, int V, int H, int Vp, int perm, cudaStream_t s) {
   dim3 grid((Vp + 31) / 32, (H + 31) / 32);
-  transpose_w_kernel<<<grid, dim3(32, 8), 0, s>>>(W, Wt, V, H, Vp);
+  transpose_w_kernel<<<grid, dim3(32, 8), 0, s>>>(W, Wt, V, H, Vp, perm);
 }
 
 void launch_joint_fwd(const Lattice& L, const JointDims& d, const CUtensorMap& tm_h, const CUtensorMap& tm_w,

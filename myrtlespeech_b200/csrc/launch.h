@@ -53,7 +53,7 @@ void launch_hgen(const Lattice& L, const __nv_bfloat16* f, const __nv_bfloat16* 
                  int n_tiles, int H, cudaStream_t s);
 
 // Wt[h][v] = W[v][h] (pitch Vp, zero padded)
-void launch_transpose_w(const __nv_bfloat16* W, __nv_bfloat16* Wt, int V, int H, int Vp, cudaStream_t s);
+void launch_transpose_w(const __nv_bfloat16* W, __nv_bfloat16* Wt, int V, int H, int Vp, int perm, cudaStream_t s);
 
 struct FwdArgs {
   const float* bias;   // [V] or null

@@ -587,51 +587,14 @@ constexpr int kMegaThreads = 512;  // 16 warps: 0..7 epilogue, 8..11 hgen / dz t
                                    // 14, 15 post warps of the kept-logits schedule (idle otherwise)
 
 // ---- dh-pass reductions in registers -------------------------------------------------------------------
-// A producer epilogue warp holds 32 tile rows: lane = 8 * (frame & 3) + label position.  df sums a column over
-// the 8 label positions of a frame (lane bits 0..2), dg over the frames (lane bits 3, 4 inside the warp, then over
-// the four warps of the set through shared memory).  Both run as halving butterflies: in each step a lane keeps
-// half of its columns, sends the other half to its partner and adds what it receives, so 32 columns take
-// 16 + 8 + 4 shuffles instead of 32 x 3 and every lane ends up owning a distinct, contiguous group of columns.
-// (The first design staged a 128 x 64 fp32 tile per set in shared memory and reduced it with two CTA-set barriers
-// per 64 columns: 9.7 k cycles per 256-column chunk, the bound of the V = 29 workload's backward pass.)
+// History of the dh epilogue's tile reductions (df sums a column over the 8 label positions of a frame, dg over the 16
+// frames), cycles per 256-column chunk at the target shape:
+//   round 1   fp32 tile of 128 x 64 per set in shared memory, two CTA-set barriers per 64 columns         9.7 k (V = 29)
+//   round 2a  lane = tile row (32x32b TMEM loads); halving shuffle butterflies for both sums: 52 shuffles, 104 selects
+//             per 32 columns                                                                               8.0 k
+//   round 2b  16x256b fragment loads: a lane holds one label position of four frames, dg's in-warp part is register adds,
+//             one butterfly of 28 shuffles for df (see the epilogue below)                                  5.7 k
 __device__ __forceinline__ float shfl_xor_f(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-
-// out[0..4): columns 4 * (lane & 7) .. + 3, summed over the 8 lanes of this lane's frame
-__device__ __forceinline__ void reduce_over_positions(const float (&v)[32], int lane, float (&out)[4]) {
-  float a[16], b[8];
-  const bool h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float keep = h4 ? v[16 + i] : v[i], send = h4 ? v[i] : v[16 + i];
-    a[i] = keep + shfl_xor_f(send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float keep = h2 ? a[8 + i] : a[i], send = h2 ? a[i] : a[8 + i];
-    b[i] = keep + shfl_xor_f(send, 2);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float keep = h1 ? b[4 + i] : b[i], send = h1 ? b[i] : b[4 + i];
-    out[i] = keep + shfl_xor_f(send, 1);
-  }
-}
-
-// out[0..8): columns 8 * (lane >> 3) .. + 7, summed over the 4 frames this warp holds for this lane's label position
-__device__ __forceinline__ void reduce_over_frames(const float (&v)[32], int lane, float (&out)[8]) {
-  float a[16];
-  const bool h16 = lane & 16, h8 = lane & 8;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float keep = h16 ? v[16 + i] : v[i], send = h16 ? v[i] : v[16 + i];
-    a[i] = keep + shfl_xor_f(send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float keep = h8 ? a[8 + i] : a[i], send = h8 ? a[i] : a[8 + i];
-    out[i] = keep + shfl_xor_f(send, 8);
-  }
-}
 
 // ---- dz of one tile from the logits the forward pass kept ------------------------------------------------------------
 // When the forward pass stored the base-2 logits z2 = log2(e) (W h + bias) as fp16, dz = c0 2^(z2 - lse2) - [blank] c1 -
@@ -1098,27 +1061,42 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         }
 
         // ---- dh pass: set `half` owns the 32-column groups g = 4*half .. 4*half + 3 of every 256-column chunk ----
+        // The accumulator is read in the 16x256b fragment layout: a thread then holds ONE label position (pos = lane / 4) of
+        // all FOUR frames of its warp (two loads of 16 TMEM lanes: rows pos and pos + 8 of each) for eight accumulator
+        // columns (8 a + 2 cq + {0, 1}, a = 0..3, cq = lane % 4) -- which are the eight contiguous columns 8 cq .. 8 cq + 7 of
+        // H, because the rows of W^T are permuted inside groups of 32 (joint.cu::transpose_w_kernel).  The sum over the warp's
+        // frames (dg) is three register adds per column and only the sum over the eight label positions (df) crosses lanes:
+        // 28 shuffles per 32 columns instead of the 52 of the lane-per-row layout (a warp issues a shuffle every ~8 cycles:
+        // scripts/micro/butterfly_rate.cu); h, df and dg move in 16-byte accesses.
         {
           named_bar_sync(set_bar, kEpiThreads);  // every warp of the set is done with its dz staging (TMA reads finished)
-          const __nv_bfloat16* hrow = keep ? p.hkeep + (static_cast<size_t>(tile) * kBM + r) * p.H
-                                           : p.h_ring + (static_cast<size_t>(ring_row) + r) * p.H;
+          const int pos = lane >> 2, cq = lane & 3;
+          // row quad*32 + 8 k + pos of the tile = frame 4*quad + k, label position pos
+          const __nv_bfloat16* hrow0 = (keep ? p.hkeep + static_cast<size_t>(tile) * kBM * p.H
+                                             : p.h_ring + static_cast<size_t>(ring_row) * p.H) +
+                                       static_cast<size_t>(quad * 32 + pos) * p.H + 8 * cq;
           // partial dg sums of the set's four warps: [group 4][quad 4][label position 8][32 columns] fp32 = 16 KB, the
-          // eight 16-byte chunks of a row XOR-swizzled with the label position (conflict-free 128-bit accesses)
+          // eight 16-byte chunks of a row XOR-swizzled with the label position
           const uint32_t part_s = smem_u32(set_base);
-          const int dtl = lane >> 3;                       // frame inside this warp's four
-          const bool t_ok = !ghost && (ti.t0 + dt < ti.T);
+          const bool hiA = lane & 16, hiB = lane & 8, hiC = lane & 4;
+          const int kdf = (hiA ? 2 : 0) + (hiB ? 1 : 0);    // the frame (of the warp's four) whose df this lane ends up with
+          const bool t_ok = !ghost && (ti.t0 + 4 * quad + kdf < ti.T);
+          float* df_row = p.df + (static_cast<size_t>(ti.b) * p.L.Tmax + ti.t0 + 4 * quad + kdf) * p.H + 8 * cq + (hiC ? 4 : 0);
           auto groups_of = [&](int jj) {                   // 32-column groups of chunk jj this set owns (uniform in the set)
             int lim = p.nc_h < p.H - jj * p.nc_h ? p.nc_h : p.H - jj * p.nc_h;   // columns of the chunk that exist
             int n = (lim - 128 * half + 31) / 32;
             return n < 0 ? 0 : (n > 4 ? 4 : n);
           };
-          auto load_h = [&](int jj, int gi, uint4 (&hv)[4]) {
+          auto load_h = [&](int jj, int gi, uint32_t (&hv)[16]) {   // hv[4 k + a]: frame k, columns c0 + 8 cq + 2 a, + 1
             const int c0 = jj * p.nc_h + (4 * half + gi) * 32;
-            const uint4* hp = reinterpret_cast<const uint4*>(hrow + c0);
+            const bool ok = c0 + 8 * cq < p.H && !(p.dbg & 512);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) hv[q] = (c0 + 8 * q < p.H && !(p.dbg & 512)) ? ld_ca_u4(hp + q) : make_uint4(0, 0, 0, 0);
+            for (int k = 0; k < 4; ++k) {
+              const uint4 q = ok ? ld_ca_u4(hrow0 + static_cast<size_t>(8 * k) * p.H + c0) : make_uint4(0, 0, 0, 0);
+              hv[4 * k] = q.x; hv[4 * k + 1] = q.y; hv[4 * k + 2] = q.z; hv[4 * k + 3] = q.w;
+            }
           };
-          uint4 hcur[4];
+          uint32_t hcur[16];
           if (groups_of(0) > 0) load_h(0, 0, hcur);
 #ifdef RNNT_PROFILE
           long long q_tm = 0, q_math = 0, q_red = 0, q_b1 = 0, q_fin = 0, q_b2 = 0, q_wait = 0;
@@ -1145,8 +1123,9 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             }
             for (int gi = 0; gi < n_g; ++gi) {
               const int c0 = j * p.nc_h + (4 * half + gi) * 32;
-              uint32_t raw[32];
-              tmem_ld32(lane_taddr + buf * kNCmax + (4 * half + gi) * 32, raw);
+              uint32_t ra[16], rb[16];     // frames 0, 1 (TMEM lanes quad*32 + 0..15) and 2, 3 (lanes + 16..31)
+              tmem_ld_16x256b_x4(lane_taddr + buf * kNCmax + (4 * half + gi) * 32, ra);
+              tmem_ld_16x256b_x4(lane_taddr + (16u << 16) + buf * kNCmax + (4 * half + gi) * 32, rb);
               tmem_ld_wait();
               QT(q_tm);
               if (gi == n_g - 1) {   // the accumulator buffer is free as soon as this set's last group is in registers
@@ -1157,44 +1136,63 @@ bwd_mega_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 ep_hold_dh += clock64() - eh_t0;
 #endif
               }
-              uint4 hnext[4];
+              uint32_t hnext[16];
               if (gi + 1 < n_g) {
                 load_h(j, gi + 1, hnext);
               } else if (j + 1 < p.n_chunks_h && groups_of(j + 1) > 0) {
                 load_h(j + 1, 0, hnext);
               } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) hnext[q] = make_uint4(0, 0, 0, 0);
+                for (int q = 0; q < 16; ++q) hnext[q] = 0u;
               }
-              float v[32];
+              // v[k][i] = dh (1 - h^2) at frame k, column c0 + 8 cq + i  (i = 2 a + e: accumulator column 8 a + 2 cq + e)
+              float v[4][8];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint32_t w[4] = {hcur[q].x, hcur[q].y, hcur[q].z, hcur[q].w};
+              for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float h0 = bf16lo(w[e]), h1 = bf16hi(w[e]);
-                  const float d0 = __uint_as_float(raw[8 * q + 2 * e]);
-                  const float d1 = __uint_as_float(raw[8 * q + 2 * e + 1]);
-                  v[8 * q + 2 * e] = fmaf(-h0 * h0, d0, d0);
-                  v[8 * q + 2 * e + 1] = fmaf(-h1 * h1, d1, d1);
+                for (int a = 0; a < 4; ++a) {
+                  const uint32_t hw = hcur[4 * k + a];
+                  const float h0 = bf16lo(hw), h1 = bf16hi(hw);
+                  const float d0 = __uint_as_float(k < 2 ? ra[4 * a + 2 * k] : rb[4 * a + 2 * (k - 2)]);
+                  const float d1 = __uint_as_float(k < 2 ? ra[4 * a + 2 * k + 1] : rb[4 * a + 2 * (k - 2) + 1]);
+                  v[k][2 * a] = fmaf(-h0 * h0, d0, d0);
+                  v[k][2 * a + 1] = fmaf(-h1 * h1, d1, d1);
                 }
               }
               QT(q_math);
-              {  // df: this lane ends up with columns c0 + 4*du .. + 3 of its own frame, summed over the label positions
-                float o[4];
-                reduce_over_positions(v, lane, o);
-                if (t_ok && c0 + 4 * du < p.H && !(p.dbg & 4096))
-                  red_add_v4_f32(p.df + (static_cast<size_t>(ti.b) * p.L.Tmax + ti.t0 + dt) * p.H + c0 + 4 * du, o[0], o[1], o[2], o[3]);
+              {  // dg: this lane's label position, summed over the warp's four frames, in registers
+                const uint32_t prow = part_s + (((gi * 4 + quad) * 8 + pos) << 7);
+                float sg[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sg[i] = (v[0][i] + v[1][i]) + (v[2][i] + v[3][i]);
+                sts128f(prow + (((2 * cq) ^ pos) << 4), sg[0], sg[1], sg[2], sg[3]);
+                sts128f(prow + (((2 * cq + 1) ^ pos) << 4), sg[4], sg[5], sg[6], sg[7]);
               }
-              {  // dg: columns c0 + 8*dtl .. + 7 of this lane's label position, summed over the warp's four frames
-                float o[8];
-                reduce_over_frames(v, lane, o);
-                const uint32_t prow = part_s + (((gi * 4 + quad) * 8 + du) << 7);
-                sts128f(prow + (((2 * dtl) ^ du) << 4), o[0], o[1], o[2], o[3]);
-                sts128f(prow + (((2 * dtl + 1) ^ du) << 4), o[4], o[5], o[6], o[7]);
+              {  // df: halving butterfly over the eight label positions (lane bits 4, 3, 2): the lane keeps two frames, then one,
+                 // then half of its columns, and ends up with frame kdf, columns c0 + 8 cq + 4 hiC + 0..3
+                float x[2][8], y[8], z[4];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float keepv = hiA ? v[2 + k][i] : v[k][i], send = hiA ? v[k][i] : v[2 + k][i];
+                    x[k][i] = keepv + shfl_xor_f(send, 16);
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float keepv = hiB ? x[1][i] : x[0][i], send = hiB ? x[0][i] : x[1][i];
+                  y[i] = keepv + shfl_xor_f(send, 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float keepv = hiC ? y[4 + i] : y[i], send = hiC ? y[i] : y[4 + i];
+                  z[i] = keepv + shfl_xor_f(send, 4);
+                }
+                if (t_ok && c0 + 8 * cq < p.H && !(p.dbg & 4096)) red_add_v4_f32(df_row + c0, z[0], z[1], z[2], z[3]);
               }
 #pragma unroll
-              for (int q = 0; q < 4; ++q) hcur[q] = hnext[q];
+              for (int q = 0; q < 16; ++q) hcur[q] = hnext[q];
               QT(q_red);
             }
             named_bar_sync(set_bar, kEpiThreads);  // the four warps' partial sums of this chunk are in shared memory
