@@ -473,7 +473,7 @@ def main():
                         "hw_achieved": kernels[dom]["hw_tflops"],
                         "hw_frac": round(kernels[dom]["hw_tflops"] / peaks["tflops_sustained"], 4),
                         "hw_frac_of_burst": round(kernels[dom]["hw_tflops"] / peaks["tflops_burst"], 4),
-                        "traffic": ncu_traffic(dom, args.workload),
+                        "traffic": ncu_traffic(dom, args.workload + ("" if kept_bytes else "_recompute")),
                         "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, per launch)",
                         "peak_source": peaks["source"] + ": the SUSTAINED cuBLAS figure, because the kernel's duration is the mean "
                                        f"over the {args.steps} launches of the timed loop (events around each launch, GPU under the "
