@@ -255,7 +255,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank-asymmetric collective should fail in minutes, not after NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     lib = _lib.load()
     peaks = load_peaks()
     from myrtlespeech_b200 import functional as Fk
@@ -418,18 +420,19 @@ def main():
             n2 = (ctypes.c_int * 2)()
             if lib.rnnt_debug_read_active_tiles(ws.data_ptr(), Bl, fd.shape[1], gd.shape[1] - 1, V, H, n2) == 0 and n2[1] > 0:
                 tiles = {"walked": int(n2[0]), "total": int(n2[1]), "fraction": round(n2[0] / n2[1], 4)}
-        # A/B in alternating blocks (the part's thermal state drifts by several per cent over a run: a single block timed
-        # after the main loop compares two different clocks, not two schedules)
-        ab = {0: 0.0, -1: 0.0}
-        for _ in range(3):
-            for mode in (-1, 0):
-                lib.rnnt_debug_set(b"prune", mode)
-                for _ in range(2):
-                    hot_step()
-                ab[mode] += timed(hot_step, 5)
-        lib.rnnt_debug_set(b"prune", 0)
-        no_skip_ms = ab[-1] / 15
-        skip_ab_ms = ab[0] / 15
+    # A/B in alternating blocks (the part's thermal state drifts by several per cent over a run: a single block timed
+    # after the main loop compares two different clocks, not two schedules).  EVERY rank runs it: hot_step contains the
+    # gradient all-reduce, a collective all ranks must enter (rank 0's figures are the ones reported).
+    ab = {0: 0.0, -1: 0.0}
+    for _ in range(3):
+        for mode in (-1, 0):
+            lib.rnnt_debug_set(b"prune", mode)
+            for _ in range(2):
+                hot_step()
+            ab[mode] += timed(hot_step, 5)
+    lib.rnnt_debug_set(b"prune", 0)
+    no_skip_ms = ab[-1] / 15
+    skip_ab_ms = ab[0] / 15
     barrier()
 
     n_rows_local = int((fl.long() * (yl.long() + 1)).sum())

@@ -65,12 +65,18 @@ def _state_bytes(B, Tmax, Umax, V, H):
 #: a step (include/rnnt_b200.h, ``rnnt_fused_forward_keep``).  ``RNNT_KEEP_ACTIVATIONS=0`` or
 #: ``set_keep_activations(False)`` selects the recompute schedule; so does an allocation that does not fit.
 _keep = os.environ.get("RNNT_KEEP_ACTIVATIONS", "1") != "0"
+#: Largest buffer (bytes) the operator keeps per live graph; beyond it the backward pass recomputes.  A pure function of the
+#: shapes, so that the fake (meta) implementation and the real one agree.  32 GiB default: 4.5x the target shape.
+_keep_cap = int(os.environ.get("RNNT_KEEP_MAX_BYTES", str(32 << 30)))
 
 
-def set_keep_activations(flag: bool) -> None:
-    """Choose between keeping logits and h for the backward pass (default) and recomputing them (less memory)."""
-    global _keep
+def set_keep_activations(flag: bool, max_bytes: Optional[int] = None) -> None:
+    """Choose between keeping logits and h for the backward pass (default) and recomputing them (less memory);
+    ``max_bytes`` changes the per-graph budget above which they are recomputed anyway."""
+    global _keep, _keep_cap
     _keep = bool(flag)
+    if max_bytes is not None:
+        _keep_cap = int(max_bytes)
 
 
 def _kept_bytes(B, Tmax, Umax, V, H):
@@ -82,7 +88,8 @@ def _kept_bytes(B, Tmax, Umax, V, H):
     if Vp > 4096:
         return 0
     max_tiles = B * ((Tmax + 15) // 16) * ((Umax + 1 + 7) // 8)
-    return _align1k(2 * max_tiles * 128 * Vp) + 2 * max_tiles * 128 * H
+    nbytes = _align1k(2 * max_tiles * 128 * Vp) + 2 * max_tiles * 128 * H
+    return nbytes if nbytes <= _keep_cap else 0
 
 
 def _bf16c(t: torch.Tensor) -> torch.Tensor:

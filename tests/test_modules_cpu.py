@@ -239,6 +239,12 @@ def test_custom_op_is_registered_with_a_fake_implementation():
         assert F._kept_bytes(32, 500, 100, 1024, 1024) == 0
     finally:
         F.set_keep_activations(True)
+    cap = F._keep_cap
+    F.set_keep_activations(True, max_bytes=1 << 30)          # a budget per live graph: beyond it the activations are recomputed
+    try:
+        assert F._kept_bytes(32, 500, 100, 1024, 1024) == 0 and F._kept_bytes(4, 200, 50, 29, 512) > 0
+    finally:
+        F.set_keep_activations(True, max_bytes=cap)
     with FakeTensorMode():
         f = torch.empty(3, 37, 128, device="cuda"); g = torch.empty(3, 12, 128, device="cuda")
         W = torch.empty(300, 128, device="cuda"); b = torch.empty(300, device="cuda")
