@@ -3,7 +3,9 @@
 //   fwd_persist_kernel   h = bf16(tanh(f_t + g_u)) produced in-kernel by four "hgen" warps one tile ahead
 //                        (into a per-CTA, double-buffered, L2-resident scratch), logits = h . W^T on tcgen05
 //                        (CTA pair, M = 256, TMEM double-buffered 256-column chunks), online log-softmax in
-//                        the epilogue warps; keeps only lse, lp_blank, lp_label.
+//                        the epilogue warps; keeps lse, lp_blank, lp_label -- and, when the caller passes a `kept`
+//                        buffer (rnnt_fused_forward_keep, the default of the Python operator), the base-2 logits as fp16
+//                        (TMA stores out of the epilogue) and the h tiles (written in place of the scratch).
 //
 // Per-launch costs of the slab kernels in joint.cu (launch gap, barrier init, TMEM allocation, pipeline
 // fill, un-overlapped last epilogue: ~11 us per 38 us launch, measured with %globaltimer stamps) are paid
@@ -529,10 +531,17 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 // =================================================================================================
 // Backward "mega-kernel": one launch per step.
 //
-//   producer pairs [0, P)      per pair-tile (256 lattice rows): hgen -> dz pass (logits recompute, softmax,
-//                              dz = c0*softmax - [blank]c1 - [label]c2 -> bf16 ring slot, + db) -> dh pass
-//                              (dh = dz . W, dpre = dh (1 - h^2), tile-reduced red.add into df / dg).
-//                              The pair's h and dz tiles live in an L2-resident ring slot (NS slots per pair).
+//   producer pairs [0, P)      per pair-tile (256 lattice rows): dz = c0*softmax - [blank]c1 - [label]c2 -> bf16 ring slot
+//                              (+ db), then the dh pass (dh = dz . W, dpre = dh (1 - h^2), tile-reduced red.add into
+//                              df / dg).  Two schedules for dz:
+//                                kept      the forward pass kept the logits (fp16) and h: a loader / post warp streams the
+//                                          logits through a ring of three smem boxes, four transform warps turn them
+//                                          into dz in place, two post warps store the boxes and add db; h is read from
+//                                          the kept buffer (dz_transform_tile and the "post warps" branch below);
+//                                recompute hgen warps rebuild h into the ring slot, the dz pass recomputes the logits on
+//                                          the tensor cores and the epilogue warps form dz from TMEM.
+//                              The pair's dz (and, when recomputing, h) tiles live in an L2-resident ring slot (NS per pair).
+//                              Only tiles with non-zero arc occupancy are walked (p.active_tiles, lattice.cu).
 //   consumer pairs [P, P + C)  own one 256 (V) x 512 (H) fp32 block of dW in TMEM for the WHOLE step and
 //                              stream every ring slot of their K-group through  dW += dz^T . h
 //                              (both operands MN-major straight out of the row-major slots).
