@@ -89,7 +89,9 @@ int rnnt_fused_backward(const void* f, const void* g, const void* W, const float
  * streams them back instead of running the recompute GEMM.  The buffer must stay untouched between the two calls; it is
  * the only state outside `workspace` (several live forward passes need one buffer each).  rnnt_fused_kept_bytes returns 0
  * where nothing can be kept (more than 4096 vocabulary columns); a NULL / too small buffer, or a shape the one-launch
- * backward kernel does not cover, silently selects the recompute schedule.  Gradients differ from the recompute schedule
+ * backward kernel does not cover, silently selects the recompute schedule.  A non-NULL `kept` passed to
+ * rnnt_fused_backward_kept MUST be the buffer the matching rnnt_fused_forward_keep call filled (same shapes, same lengths):
+ * the library cannot tell a filled buffer from an unfilled one.  Gradients differ from the recompute schedule
  * only through the fp16 rounding of the kept logits (relative 2^-11 on a logit, below the bf16 rounding of dz that both
  * schedules share); the blank and label columns use the exact fp32 log-probabilities in both. */
 size_t rnnt_fused_kept_bytes(int B, int Tmax, int Umax, int V, int H);
