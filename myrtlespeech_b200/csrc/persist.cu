@@ -656,6 +656,7 @@ __device__ __forceinline__ void dz_transform_tile(const BwdPArgs& p, const TileI
   // c0 2^(z2 - lse2) = +-2^(z2 - koff): the row's scale rides in the exponent (one add and one ex2 per element)
   const float koff = c0g != 0.0f ? lse2 - lg2f(fabsf(c0g)) : 1.0e30f;
   const uint32_t sgn = c0g < 0.0f ? 0x80008000u : 0u;
+  const bool any_neg = __any_sync(0xffffffffu, sgn != 0u);
   const int nbox = p.Vp >> 6;
   const int sw = ht & 7;
   for (int k = 0; k < nbox; ++k, ++q) {
@@ -677,14 +678,29 @@ __device__ __forceinline__ void dz_transform_tile(const BwdPArgs& p, const TileI
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                    : "=r"(x[c][0]), "=r"(x[c][1]), "=r"(x[c][2]), "=r"(x[c][3]) : "r"(rowp + ((c ^ sw) << 4)));
     }
+    if (!any_neg) {     // the common case (no negative upstream gradient in the warp): no sign handling at all
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const bool have = k * 64 + c * 8 < p.zcols;   // columns the forward pass wrote
+      for (int c = 0; c < 8; ++c) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 a = f16x2_to_f32(x[c][e]);
-        const uint32_t o = pack_bf16x2(ex2f(a.x - koff), ex2f(a.y - koff)) ^ sgn;
-        x[c][e] = have ? o : 0u;
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = f16x2_to_f32(x[c][e]);
+          x[c][e] = pack_bf16x2(ex2f(a.x - koff), ex2f(a.y - koff));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = f16x2_to_f32(x[c][e]);
+          x[c][e] = pack_bf16x2(ex2f(a.x - koff), ex2f(a.y - koff)) ^ sgn;
+        }
+      }
+    }
+    if (k * 64 + 64 > p.zcols) {   // last box of a vocabulary that ends inside it: columns the forward pass did not write
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (k * 64 + c * 8 >= p.zcols) { x[c][0] = 0u; x[c][1] = 0u; x[c][2] = 0u; x[c][3] = 0u; }
       }
     }
 #pragma unroll
