@@ -461,7 +461,7 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           mx = mn;
           if (static_cast<unsigned>(p.blank - c0) < 32u) zb = pick32(v, p.blank - c0);
           if (static_cast<unsigned>(label - c0) < 32u) zl = pick32(v, label - c0);
-          if (p.keep_z) {
+          if (p.keep_z && !(p.dbg & 128)) {   // bring-up: dbg & 128 = no logit staging at all (timing only)
             const uint32_t zo = (g & 1) * 2048;
             if (lane == 0) tma_store_wait_read1();   // the store that last used this slice has read it
             __syncwarp();
@@ -472,7 +472,7 @@ fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              if (!ghost) tma_store_2d(&tm_z, zsl + zo, c0, tile * kBM + lq * 32);
+              if (!ghost && !(p.dbg & 64)) tma_store_2d(&tm_z, zsl + zo, c0, tile * kBM + lq * 32);   // dbg & 64: staged, not stored
               tma_store_commit();
             }
           }
